@@ -1,0 +1,302 @@
+"""ctypes wrapper of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` leg
+may import this module.  PARITY UNPINNED: see oracle/cgo_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+STATUS = [
+    "incomplete", "success", "increasing_objective", "max_iters_reached",
+    "non_finite_objective_or_gradient_proposed", "non_descent_search_direction",
+    "linesearch_a_max_overflow", "linesearch_max_iters_reached", "zoom_max_iters_reached",
+    "accepted_non_finite_iterate", "cannot_find_initial_feasible_step", "max_step_length_reached",
+    "cannot_find_feasible_step", "non_finite_step_proposed", "proposed_step_same_as_current_step",
+    "step_bracket_precision_issue",
+]
+FLAVOURS = {"HagerZhang": 0, "YuanWangSheng": 1, "SallehAlhawarat": 2, "LiuStorrey": 3, "LBFGS": 4}
+LS_KINDS = {"StrongWolfeBisection": 0, "Wolfe": 1, "YuanWeiLuWolfe": 2, "Backtracking": 3}
+SUM_MODES = {"seq": 0, "pairwise": 1, "comp": 2, "cgo": 3}
+BETA_FORMS = {"literal": 0, "fused": 1}
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [
+        ("eps", C.c_double), ("max_iters", C.c_int64), ("flavour", C.c_int32),
+        ("lbfgs_m", C.c_int32), ("mu", C.c_double), ("ls_kind", C.c_int32), ("_pad", C.c_int32),
+        ("c1", C.c_double), ("c2", C.c_double), ("delta1", C.c_double), ("growth", C.c_double),
+        ("ls_max_iters", C.c_int64), ("zoom_max_iters", C.c_int64), ("max_step_size", C.c_double),
+        ("feas_max_iters", C.c_int64), ("discount", C.c_double), ("sum_mode", C.c_int32),
+        ("threads", C.c_int32), ("beta_form", C.c_int32), ("_pad2", C.c_int32),
+    ]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [
+        ("objective", C.c_double), ("iters_ran", C.c_int64), ("status", C.c_int32),
+        ("_pad", C.c_int32), ("trace_len", C.c_int64), ("fdf_evals_total", C.c_int64),
+    ]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libcgo_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("cgo_oracle.c", "cgo_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libcgo_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    dp = C.POINTER(C.c_double)
+    L.orc_obj_booth.restype = C.c_void_p
+    L.orc_obj_rosenbrock.restype = C.c_void_p
+    L.orc_obj_rosenbrock.argtypes = [C.c_int64]
+    L.orc_obj_rosenbrock_chained.restype = C.c_void_p
+    L.orc_obj_rosenbrock_chained.argtypes = [C.c_int64]
+    L.orc_obj_quartic_barrier.restype = C.c_void_p
+    L.orc_obj_quartic_barrier.argtypes = [C.c_int64]
+    L.orc_obj_sparse_ls_synth.restype = C.c_void_p
+    L.orc_obj_sparse_ls_synth.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int32]
+    L.orc_obj_sparse_ls_csr.restype = C.c_void_p
+    L.orc_obj_sparse_ls_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.orc_obj_logreg_synth.restype = C.c_void_p
+    L.orc_obj_logreg_synth.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_int32]
+    L.orc_obj_destroy.argtypes = [C.c_void_p]
+    L.orc_obj_dim.restype = C.c_int64
+    L.orc_obj_dim.argtypes = [C.c_void_p]
+    for name, rt in [("orc_csr_nnz", C.c_int64), ("orc_csr_nrows", C.c_int64),
+                     ("orc_csr_rowptr", C.c_void_p), ("orc_csr_col", C.c_void_p),
+                     ("orc_csr_val", C.c_void_p), ("orc_csr_b", C.c_void_p),
+                     ("orc_csrT_rowptr", C.c_void_p), ("orc_csrT_col", C.c_void_p),
+                     ("orc_csrT_val", C.c_void_p)]:
+        getattr(L, name).restype = rt
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.orc_sparse_ls_xtrue.argtypes = [C.c_int64, C.c_uint64, dp]
+    L.orc_fdf.restype = C.c_double
+    L.orc_fdf.argtypes = [C.c_void_p, dp, dp]
+    L.orc_dot.restype = C.c_double
+    L.orc_dot.argtypes = [dp, dp, C.c_int64, C.c_int, C.c_int]
+    L.orc_sum.restype = C.c_double
+    L.orc_sum.argtypes = [dp, C.c_int64, C.c_int, C.c_int]
+    L.orc_sum_cgo.restype = C.c_double
+    L.orc_sum_cgo.argtypes = [dp, C.c_int64, C.c_int, C.c_int64]
+    L.orc_set_cgo_order.argtypes = [C.c_int, C.c_int]
+    L.orc_spmv.argtypes = [C.c_void_p, C.c_int, dp, dp]
+    L.orc_hash_u01.restype = C.c_double
+    L.orc_hash_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    L.orc_rosenbrock_x0.argtypes = [C.c_int64, C.c_uint64, C.c_double, dp]
+    L.orc_minimize.restype = C.c_int
+    L.orc_minimize.argtypes = [C.c_void_p, dp, C.POINTER(OrcConfig), dp, dp, C.POINTER(OrcResult),
+                               dp, dp, dp, C.POINTER(C.c_int64)]
+    L.orc_minimize_rerun.restype = C.c_int
+    L.orc_minimize_rerun.argtypes = [C.c_void_p, dp, C.POINTER(OrcConfig), C.c_int, dp, dp,
+                                     C.POINTER(OrcResult), C.c_int64, dp, dp, dp, C.POINTER(C.c_int64)]
+    _LIB = L
+    return L
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_config(flavour="HagerZhang", linesearch="StrongWolfeBisection", eps=1e-5, max_iters=1000,
+                mu=0.1, lbfgs_m=10, c1=1e-5, c2=0.8, delta1=1e-6, growth=2.0, ls_max_iters=1000,
+                zoom_max_iters=100, max_step_size=1e12, feas_max_iters=50, discount=0.9,
+                sum_mode="seq", threads=1, beta_form="literal") -> OrcConfig:
+    """Defaults are the reference's canonical run, examples/min.jl:16-35."""
+    c = OrcConfig()
+    c.eps, c.max_iters, c.flavour, c.lbfgs_m, c.mu = eps, max_iters, FLAVOURS[flavour], lbfgs_m, mu
+    c.ls_kind, c.c1, c.c2, c.delta1, c.growth = LS_KINDS[linesearch], c1, c2, delta1, growth
+    c.ls_max_iters, c.zoom_max_iters, c.max_step_size = ls_max_iters, zoom_max_iters, max_step_size
+    c.feas_max_iters, c.discount = feas_max_iters, discount
+    c.sum_mode, c.threads, c.beta_form = SUM_MODES[sum_mode], threads, BETA_FORMS[beta_form]
+    return c
+
+
+@dataclass
+class OracleResult:
+    objective: float
+    minimizer: np.ndarray
+    gradient: np.ndarray
+    iters_ran: int
+    status: str
+    trace_objective: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    trace_grad_norm: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    trace_step_size: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    trace_objective_evals: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    fdf_evals_total: int = 0
+
+
+class Objective:
+    """Owns an ``orc_objective*``."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise ValueError("oracle objective constructor rejected its arguments")
+        self.h = C.c_void_p(handle)
+        self.n = lib().orc_obj_dim(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_obj_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # constructors ------------------------------------------------------------------
+    @staticmethod
+    def booth():
+        return Objective(lib().orc_obj_booth())
+
+    @staticmethod
+    def rosenbrock(n):
+        return Objective(lib().orc_obj_rosenbrock(n))
+
+    @staticmethod
+    def rosenbrock_chained(n):
+        return Objective(lib().orc_obj_rosenbrock_chained(n))
+
+    @staticmethod
+    def barrier(n):
+        return Objective(lib().orc_obj_quartic_barrier(n))
+
+    @staticmethod
+    def sparse_ls(n, nnz_per_row=10, W=None, seed=24, coh_log2=0, threads=1):
+        if W is None:
+            W = min(1 << 20, (n - 1) // 2)
+        return Objective(lib().orc_obj_sparse_ls_synth(n, nnz_per_row, W, seed, coh_log2, threads))
+
+    @staticmethod
+    def sparse_ls_csr(nrows, ncols, rowptr, col, val, b, threads=1):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        return Objective(lib().orc_obj_sparse_ls_csr(nrows, ncols, rowptr.ctypes.data, col.ctypes.data,
+                                                     val.ctypes.data, b.ctypes.data, threads))
+
+    @staticmethod
+    def logreg(nsamples, nfeat, nnz_per_row=20, seed=24, lam=1e-6, threads=1):
+        return Objective(lib().orc_obj_logreg_synth(nsamples, nfeat, nnz_per_row, seed, lam, threads))
+
+    # primitives --------------------------------------------------------------------
+    def fdf(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.empty(self.n)
+        f = lib().orc_fdf(self.h, _dp(g), _dp(x))
+        return f, g
+
+    def csr(self, transposed=False):
+        L = lib()
+        nnz = L.orc_csr_nnz(self.h)
+        nrows = self.n if transposed else L.orc_csr_nrows(self.h)
+        fr, fc, fv = ((L.orc_csrT_rowptr, L.orc_csrT_col, L.orc_csrT_val) if transposed
+                      else (L.orc_csr_rowptr, L.orc_csr_col, L.orc_csr_val))
+        rp = np.ctypeslib.as_array(C.cast(fr(self.h), C.POINTER(C.c_int64)), (nrows + 1,)).copy()
+        ci = np.ctypeslib.as_array(C.cast(fc(self.h), C.POINTER(C.c_int32)), (nnz,)).copy()
+        va = np.ctypeslib.as_array(C.cast(fv(self.h), C.POINTER(C.c_double)), (nnz,)).copy()
+        return rp, ci, va
+
+    def rhs(self):
+        L = lib()
+        nrows = L.orc_csr_nrows(self.h)
+        return np.ctypeslib.as_array(C.cast(L.orc_csr_b(self.h), C.POINTER(C.c_double)), (nrows,)).copy()
+
+    def spmv(self, x, transposed=False):
+        L = lib()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.n if transposed else L.orc_csr_nrows(self.h))
+        L.orc_spmv(self.h, int(transposed), _dp(x), _dp(y))
+        return y
+
+
+def dot(a, b, sum_mode="seq", threads=1):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return lib().orc_dot(_dp(a), _dp(b), a.size, SUM_MODES[sum_mode], threads)
+
+
+def set_cgo_order(G=1184, shards=1):
+    """Parameters of the canonical reduction order (include/cgoptim.h): virtual CTAs, shards."""
+    lib().orc_set_cgo_order(G, shards)
+
+
+def sum_cgo(a, U=4, align=1):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return lib().orc_sum_cgo(_dp(a), a.size, U, align)
+
+
+def hash_u01(seed, i, k):
+    return lib().orc_hash_u01(seed, i, k)
+
+
+def rosenbrock_x0(n, seed=24, perturb=0.0):
+    x0 = np.empty(n)
+    lib().orc_rosenbrock_x0(n, seed, perturb, _dp(x0))
+    return x0
+
+
+def sparse_ls_xtrue(n, seed=24):
+    x = np.empty(n)
+    lib().orc_sparse_ls_xtrue(n, seed, _dp(x))
+    return x
+
+
+def minimize(obj: Objective, x0, cfg: OrcConfig, trace=True) -> OracleResult:
+    """minimizeobjective, src/engine/optim.jl:6-171."""
+    L = lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = obj.n
+    assert x0.size == n
+    xo, go = np.empty(n), np.empty(n)
+    res = OrcResult()
+    mi = max(int(cfg.max_iters), 1)
+    tf, tg, ta = np.zeros(mi), np.zeros(mi), np.zeros(mi)
+    te = np.zeros(mi, dtype=np.int64)
+    rc = L.orc_minimize(obj.h, _dp(x0), C.byref(cfg), _dp(xo), _dp(go), C.byref(res),
+                        _dp(tf) if trace else None, _dp(tg) if trace else None,
+                        _dp(ta) if trace else None,
+                        te.ctypes.data_as(C.POINTER(C.c_int64)) if trace else None)
+    if rc != 0:
+        raise AssertionError(f"oracle config assertion failed (rc={rc})")
+    k = res.trace_len if trace else 0
+    return OracleResult(res.objective, xo, go, res.iters_ran, STATUS[res.status], tf[:k].copy(),
+                        tg[:k].copy(), ta[:k].copy(), te[:k].copy(), res.fdf_evals_total)
+
+
+def minimize_rerun(obj: Objective, x0, cfgs) -> list[OracleResult]:
+    """minimizeobjectivererun, src/engine/optim.jl:173-208; cfgs[0] primary, cfgs[1:] backups."""
+    L = lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n, k = obj.n, len(cfgs)
+    arr = (OrcConfig * k)(*cfgs)
+    stride = max(max(int(c.max_iters) for c in cfgs), 1)
+    xo, go = np.empty((k, n)), np.empty((k, n))
+    res = (OrcResult * k)()
+    tf, tg, ta = np.zeros((k, stride)), np.zeros((k, stride)), np.zeros((k, stride))
+    te = np.zeros((k, stride), dtype=np.int64)
+    nret = L.orc_minimize_rerun(obj.h, _dp(x0), arr, k, _dp(xo), _dp(go), res, stride, _dp(tf),
+                                _dp(tg), _dp(ta), te.ctypes.data_as(C.POINTER(C.c_int64)))
+    if nret < 0:
+        raise AssertionError(f"oracle config assertion failed (rc={nret})")
+    out = []
+    for i in range(nret):
+        t = res[i].trace_len
+        out.append(OracleResult(res[i].objective, xo[i].copy(), go[i].copy(), res[i].iters_ran,
+                                STATUS[res[i].status], tf[i, :t].copy(), tg[i, :t].copy(),
+                                ta[i, :t].copy(), te[i, :t].copy(), res[i].fdf_evals_total))
+    return out
