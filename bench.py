@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — CG iterations/s on the BASELINE.json workloads, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload sparse_ls|rosenbrock] [--n N] [--coh C]
+
+A "step" is one iteration of the `for n = 1:max_iters` body of minimizeobjective
+(src/engine/optim.jl:50-160): one strong-Wolfe line search (>= 1 fdf! trial) + getβ + the
+state roll + updatedir!.  The workload is BASELINE.json's metric config: sparse least squares
+½‖Ax−b‖², CSR A 2e8×2e8 with 10 nnz/row, FP64 Hager-Zhang CG (configs[2]; it fits one B200);
+`--workload rosenbrock` runs configs[1] (extended Rosenbrock n = 1e8).  Under torchrun the rows
+/ vector slices are sharded over the ranks (total work fixed: "strong" scaling).
+
+`--impl reference` times the reference's CPU path — oracle/ (the C restatement; Julia is not
+installed here or on the GPU box) in the reference's own shape: unfused passes, allocating
+getβ, sequential sums — on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FULL_N = {"sparse_ls": 200_000_000, "rosenbrock": 100_000_000}
+SAMPLE_N = {"sparse_ls": 4_000_000, "rosenbrock": 20_000_000}   # CPU-arm sample sizes
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="sparse_ls", choices=["sparse_ls", "rosenbrock"])
+    p.add_argument("--n", type=int, default=0, help="problem size (default: BASELINE.json's)")
+    p.add_argument("--coh", type=int, default=0, help="sparse_ls generator: log2 rows sharing offsets")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------ workloads
+def solver_configs(cg, max_iters):
+    # examples/min.jl:16-35: HagerZhang, StrongWolfeBisection(c1=1e-5, c2=0.8, growth 2, 1000, 100).
+    # ϵ is set far below reach so that W+K iterations always run (the metric is iterations/s).
+    cfg = cg.setupCGConfig(1e-300, cg.HagerZhang(), cg.EnableTrace(), max_iters=max_iters)
+    ls = cg.setupStrongWolfeBisection(1e-5, 0.8, a_max_growth_factor=2.0, max_iters=1000, zoom_max_iters=100)
+    return cfg, ls
+
+
+def make_objective(cg, args, ctx, n):
+    if args.workload == "rosenbrock":
+        obj = cg.RosenbrockGPU(n, ctx)
+        x0 = obj.default_x0(24, 0.1)
+    else:
+        obj = cg.SparseLSGPU(n, 10, None, 24, args.coh, ctx)
+        x0 = np.zeros(obj.n_local)
+    return obj, x0
+
+
+def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
+    """SURVEY.md §8(d) / DESIGN.md: algorithmic HBM bytes of `iters` iterations with `evals`
+    fdf! trials on one rank (fused minimum)."""
+    if args.workload == "rosenbrock":
+        # first trial of an iteration also applies updatedir!: R x,g,u W u,xp,g⁺ = 48n; later 40n
+        return 8.0 * n_local * (6 * iters + 5 * (evals - iters))
+    per_eval = 2 * (12.0 * nnz_local + 8.0 * (n_local + 1)) + 72.0 * n_local
+    return evals * per_eval + 48.0 * n_local * iters
+
+
+def run_ours(args):
+    import torch
+    import cgoptim_b200 as cg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = cg.Context(local_rank)
+    if world > 1:
+        ctx.comm_init_torch()
+    n = args.n or FULL_N[args.workload]
+    K, W = args.steps, args.warmup
+    obj, x0 = make_objective(cg, args, ctx, n)
+    n_local = obj.n_local
+    nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
+    cfg, ls = solver_configs(cg, W + K + 1)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    run = cg.MinimizerRun(obj, x0, cfg, ls)
+    for _ in range(W):
+        assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
+    ctx.timing(True)
+    ctx.timing_read(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.kernel_launches
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        assert run.step() is None, f"run ended inside the timed region: {run.ret.status}"
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    timers = ctx.timing_read(reset=True)
+    ctx.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    evals = int(run.ret.trace.objective_evals[W:W + K].sum())
+    trace_f = run.ret.trace.objective[:W + K].copy()
+    run.info.close()
+
+    # dominant kernel roofline (CUDA events on the launching stream, inside the timed region)
+    peak, peak_src = peaks()
+    if args.workload == "rosenbrock":
+        dom = "trial"
+        dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
+        dom_ms, dom_cnt = timers["trial"]
+    else:
+        dom = "spmv+spmvT"
+        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
+        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
+        # per SpMV launch: matrix (12 nnz + 8(n+1)) + gather 8n + R 8n (b / u) + W 8n  
+        dom_bytes = (dom_cnt / 2.0) * (2 * (12.0 * nnz_local + 8.0 * (n_local + 1)) + 48.0 * n_local)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    total_bytes = algorithmic_bytes(args, n_local, nnz_local, evals, K)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
+                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+                "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
+                "kernel_share_of_step": round(dom_ms / ms, 4),
+                "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}}
+
+    # ---------------- end-to-end through the public API (`e2e`) ----------------
+    e2e = None
+    if not args.no_e2e:
+        cfg2, ls2 = solver_configs(cg, K)
+        x0p = torch.from_numpy(x0.copy()).pin_memory().numpy()
+        barrier()
+        t0 = time.perf_counter()
+        ret = cg.minimizeobjective(obj, x0p, cfg2, ls2)      # H2D x0 … K iterations … D2H x, g
+        barrier()
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        dt = float(tdt.item())
+        assert ret.iters_ran == K, (ret.iters_ran, ret.status)
+        ev2 = int(ret.trace.objective_evals.sum())
+        e2e = {"value": round(K / dt, 4), "unit": "iterations/s",
+               "h2d_bytes_per_step": round((8.0 * n_local + 16.0 * (ev2 + K)) / K, 1),
+               "d2h_bytes_per_step": round((16.0 * n_local + 128.0 * (ev2 + 2 * K)) / K, 1),
+               "includes": "x0 H2D from pinned host memory, f/g at x0, K iterations (scalar pack D2H "
+                           "every launch), minimizer+gradient D2H", "wall_s": round(dt, 4)}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "cg_iterations_per_s", "value": round(K / (ms * 1e-3), 4), "unit": "iterations/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": (f"sparse least-squares 0.5||Ax-b||^2, CSR {n}x{n}, 10 nnz/row (banded-random, "
+                                    f"seed 24, coh_log2={args.coh}), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
+                                    if args.workload == "sparse_ls" else
+                                    f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
+                       "n": n, "sharding": f"rows/vector slices over {world} rank(s)",
+                       "l2_policy": "inputs larger than L2 (vectors are 8n bytes >> 126 MB)",
+                       "fdf_evals_in_timed_region": evals, "host": "python/ctypes over the C ABI"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "host_wall_ms_per_step": round(wall_ms / K, 4),
+            "objective_trace_head": [float(v) for v in trace_f[:4]],
+        }
+    return line, ctx
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def run_cpu(args, steps, warmup, threads):
+    """The reference's CPU path (oracle restatement, reference-shaped) on a bounded sample."""
+    from oracle import oracle as O
+    n_full = args.n or FULL_N[args.workload]
+    n = min(SAMPLE_N[args.workload], n_full)
+    if args.workload == "rosenbrock":
+        obj = O.Objective.rosenbrock(n)
+        x0 = O.rosenbrock_x0(n, 24, 0.1)
+    else:
+        obj = O.Objective.sparse_ls(n, 10, min(1 << 20, (n - 1) // 2), 24, args.coh, threads)
+        x0 = np.zeros(n)
+    mk = lambda it: O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-300, max_iters=it,
+                                  sum_mode="seq", beta_form="literal", threads=threads)
+    if warmup:
+        O.minimize(obj, x0, mk(warmup), trace=False)
+    t0 = time.perf_counter()
+    r = O.minimize(obj, x0, mk(steps))
+    dt = time.perf_counter() - t0
+    its = r.iters_ran
+    # one fdf! at x0 is inside the timed call, as in minimizeobjective
+    rate_sample = its / dt
+    return {"value": rate_sample * (n / n_full), "unit": "iterations/s", "cores": threads, "kind": "port",
+            "sample": (f"oracle C restatement of the reference (Julia not installed: 'julia thread count' n/a), "
+                       f"reference-shaped arithmetic, {its} iterations at n={n} in {dt:.2f}s = {rate_sample:.3f} it/s, "
+                       f"scaled linearly by n/n_full = {n}/{n_full}; OpenMP threads on fdf! and dot/norm = {threads}"),
+            "sample_n": n, "sample_iterations_per_s": rate_sample, "host_cores": os.cpu_count()}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        cb = run_cpu(args, max(args.steps, 1), min(args.warmup, 1), threads)
+        n = args.n or FULL_N[args.workload]
+        line = {"impl": "reference", "metric": "cg_iterations_per_s", "value": round(cb["value"], 6),
+                "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(1e3 / cb["value"], 3), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "n": n, "sample_n": cb["sample_n"]},
+                "cpu_baseline": cb,
+                "e2e": {"value": round(cb["value"], 6), "unit": "iterations/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    line, ctx = run_ours(args)
+    if rank == 0:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = run_cpu(args, 5, 0, os.cpu_count() or 1)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,647 @@
+// blas1.cu — the fused BLAS-1 chain of the CG iteration and the solver-state C ABI.
+//
+// One templated streaming kernel (k_blas1) drives every elementwise op: 128-bit coalesced
+// loads (U = 4 in flight per input vector per lane), unfused IEEE arithmetic (-fmad=false: the
+// reference's Julia loops do not contract a*b+c), canonical-order reductions
+// (reduce.cuh).  Ops:
+//   RosenTrial<FUSED>  evalϕdϕ! (src/cg_utils.jl:3-22) for the extended Rosenbrock objective,
+//                      fused with norm(df_xp) (src/engine/optim.jl:107) and every dot of getβ
+//                      (src/cg_flavours.jl:51-170); FUSED also does updatedir! (:2-15) first.
+//   DirUpdate          updatedir! u = −g + βu (cg_flavours.jl:2-15) + next dot(df_x,u)
+//                      (nocedal.jl:56, wolfe.jl:40, geometric.jl:43) + dot(u,u) (wolfe.jl:240)
+//   ResetDir           u = −g (cg_flavours.jl:28, wolfe.jl:129)
+//   BetaLiteral        Σ (y_i − m u_i)(g⁺_i / R)  (cg_flavours.jl:71-76, :100-105, as written)
+//   NormUPlusG         ‖u + df_x‖² (wolfe.jl:123)
+//   AxpyDir            xp = x + a u [after u = −g + βu] for multi-kernel (CSR) objectives
+//   L-BFGS ops         stage (s,y), two-loop recursion steps (N&W Alg 7.4)
+#include "internal.cuh"
+#include "reduce.cuh"
+
+// ------------------------------------------------------------------ generic streaming kernel
+template <class Op>
+__global__ void __launch_bounds__(CGO_B, Op::OCC) k_blas1(Op op, int64_t n, RedArgs red) {
+    constexpr int K = Op::K;
+    __shared__ double sm[K * CGO_NW];
+    const int64_t nq = (n + 1) >> 1;
+    constexpr int64_t tileq = (int64_t)CGO_B * CGO_U_VEC;
+    const int64_t ntiles = (nq + tileq - 1) / tileq;
+    const int nact = (int)(ntiles < (int64_t)red.G ? ntiles : (int64_t)red.G);
+    op.prologue();
+    for (int v = blockIdx.x; v < nact; v += gridDim.x) {
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int64_t tile = v; tile < ntiles; tile += red.G) {
+            const int64_t q0 = tile * tileq + threadIdx.x;
+            typename Op::In in[CGO_U_VEC];
+#pragma unroll
+            for (int j = 0; j < CGO_U_VEC; ++j) {
+                const int64_t q = q0 + (int64_t)j * CGO_B;
+                if (q < nq) in[j] = op.load(q);
+            }
+#pragma unroll
+            for (int j = 0; j < CGO_U_VEC; ++j) {
+                const int64_t q = q0 + (int64_t)j * CGO_B;
+                if (q < nq) op.apply(q, in[j], acc, 2 * q + 1 < n);
+            }
+        }
+        cgo_cta_combine<K>(acc, sm);
+        cgo_publish<K>(red, v, acc);
+    }
+    cgo_grid_finish<K>(red, nact, sm);
+}
+
+template <class Op>
+static int launch_blas1(cgo_ctx *c, const Op &op, int64_t n, const RedArgs &red) {
+    const int64_t nq = (n + 1) >> 1;
+    const int64_t tileq = (int64_t)CGO_B * CGO_U_VEC;
+    int64_t ntiles = (nq + tileq - 1) / tileq;
+    int64_t nact = ntiles < red.G ? ntiles : red.G;
+    int64_t phys = (int64_t)c->sms * Op::OCC;
+    int grid = (int)(nact < phys ? nact : phys);
+    if (grid < 1) grid = 1;
+    cgo_timer_begin(c, Op::TCLASS);
+    k_blas1<Op><<<grid, CGO_B, 0, c->stream>>>(op, n, red);
+    cgo_timer_end(c);
+    c->launches++;
+    CGO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__device__ __forceinline__ double2 ld2rw(const double2 *p) {   // vectors updated in place
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+// ------------------------------------------------------------------ ops
+// extended Rosenbrock trial.  Elementwise spec (bit-for-bit the oracle's rosen_fdf):
+//   t = x2 − x1*x1; om = 1 − x1; f = (100 t) t + om om; g1 = (−400 x1) t − 2 om; g2 = 200 t
+template <bool FUSED>
+struct RosenTrial {
+    static constexpr int TCLASS = CGO_T_TRIAL;
+    static constexpr int K = 9;
+    static constexpr int OCC = 2;
+    struct In { double2 x, u, g; };
+    const double2 *x, *g;
+    double2 *u;
+    double2 *xp, *gp;
+    double a, beta;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.x = cgo_ld2(x + q);
+        r.g = cgo_ld2(g + q);
+        r.u = FUSED ? ld2rw(u + q) : cgo_ld2(u + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool) const {
+        double2 uu = in.u;
+        if (FUSED) {                                   // updatedir!, cg_flavours.jl:10-12
+            uu.x = -in.g.x + beta * in.u.x;
+            uu.y = -in.g.y + beta * in.u.y;
+            cgo_st2(u + q, uu);
+        }
+        double2 p;                                     // cg_utils.jl:13-15
+        p.x = in.x.x + a * uu.x;
+        p.y = in.x.y + a * uu.y;
+        cgo_st2(xp + q, p);
+        const double t = p.y - p.x * p.x;
+        const double om = 1.0 - p.x;
+        const double f = (100.0 * t) * t + om * om;
+        double2 gn;
+        gn.x = (-400.0 * p.x) * t - 2.0 * om;
+        gn.y = 200.0 * t;
+        cgo_st2(gp + q, gn);
+        const double y1 = gn.x - in.g.x, y2 = gn.y - in.g.y;
+        acc[CGO_P_PHI] = acc[CGO_P_PHI] + f;
+        acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.x * uu.x;   acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.y * uu.y;
+        acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.x * gn.x;   acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.y * gn.y;
+        acc[CGO_P_YY] = acc[CGO_P_YY] + y1 * y1;           acc[CGO_P_YY] = acc[CGO_P_YY] + y2 * y2;
+        acc[CGO_P_UY] = acc[CGO_P_UY] + uu.x * y1;         acc[CGO_P_UY] = acc[CGO_P_UY] + uu.y * y2;
+        acc[CGO_P_YGP] = acc[CGO_P_YGP] + y1 * gn.x;       acc[CGO_P_YGP] = acc[CGO_P_YGP] + y2 * gn.y;
+        acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.x * in.g.x;   acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.y * in.g.y;
+        acc[CGO_P_UG] = acc[CGO_P_UG] + uu.x * in.g.x;     acc[CGO_P_UG] = acc[CGO_P_UG] + uu.y * in.g.y;
+        acc[CGO_P_UU] = acc[CGO_P_UU] + uu.x * uu.x;       acc[CGO_P_UU] = acc[CGO_P_UU] + uu.y * uu.y;
+    }
+};
+
+// u = −g + βu (RESET: u = −g); pack {g·u, u·u}
+template <bool RESET>
+struct DirUpdate {
+    static constexpr int TCLASS = CGO_T_DIR;
+    static constexpr int K = 2;
+    static constexpr int OCC = 4;
+    struct In { double2 g, u; };
+    const double2 *g;
+    double2 *u;
+    double beta;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.g = cgo_ld2(g + q);
+        if (!RESET) r.u = ld2rw(u + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 un;
+        if (RESET) { un.x = -in.g.x; un.y = -in.g.y; }
+        else { un.x = -in.g.x + beta * in.u.x; un.y = -in.g.y + beta * in.u.y; }
+        if (!v2) un.y = 0.0;
+        cgo_st2(u + q, un);
+        acc[CGO_D_GU] = acc[CGO_D_GU] + in.g.x * un.x;
+        acc[CGO_D_UU] = acc[CGO_D_UU] + un.x * un.x;
+        if (v2) {
+            acc[CGO_D_GU] = acc[CGO_D_GU] + in.g.y * un.y;
+            acc[CGO_D_UU] = acc[CGO_D_UU] + un.y * un.y;
+        }
+    }
+};
+
+// Σ (y_i − m u_i)(g⁺_i / R) with y = g⁺ − g: tmp2 = g_next ./ R; tmp1 = y − m .* u; dot(tmp1,tmp2)
+struct BetaLiteral {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 2;
+    struct In { double2 gp, g, u; };
+    const double2 *gp, *g, *u;
+    double R, m;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.gp = cgo_ld2(gp + q); r.g = cgo_ld2(g + q); r.u = cgo_ld2(u + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        const double y1 = in.gp.x - in.g.x;
+        const double t2a = in.gp.x / R;
+        const double t1a = y1 - m * in.u.x;
+        acc[0] = acc[0] + t1a * t2a;
+        if (v2) {
+            const double y2 = in.gp.y - in.g.y;
+            const double t2b = in.gp.y / R;
+            const double t1b = y2 - m * in.u.y;
+            acc[0] = acc[0] + t1b * t2b;
+        }
+    }
+};
+
+struct NormUPlusG {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 4;
+    struct In { double2 g, u; };
+    const double2 *g, *u;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.g = cgo_ld2(g + q); r.u = cgo_ld2(u + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        const double t1 = in.u.x + in.g.x;
+        acc[0] = acc[0] + t1 * t1;
+        if (v2) { const double t2 = in.u.y + in.g.y; acc[0] = acc[0] + t2 * t2; }
+    }
+};
+
+// xp = x + a u, optionally after u = −g + βu; pack {g·u, u·u, xp·xp}
+template <bool FUSED>
+struct AxpyDir {
+    static constexpr int TCLASS = CGO_T_AXPY;
+    static constexpr int K = 3;
+    static constexpr int OCC = 2;
+    struct In { double2 x, u, g; };
+    const double2 *x, *g;
+    double2 *u, *xp;
+    double a, beta;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.x = cgo_ld2(x + q);
+        r.g = cgo_ld2(g + q);
+        r.u = FUSED ? ld2rw(u + q) : cgo_ld2(u + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 uu = in.u;
+        if (FUSED) {
+            uu.x = -in.g.x + beta * in.u.x;
+            uu.y = v2 ? -in.g.y + beta * in.u.y : 0.0;
+            cgo_st2(u + q, uu);
+        }
+        double2 p;
+        p.x = in.x.x + a * uu.x;
+        p.y = v2 ? in.x.y + a * uu.y : 0.0;
+        cgo_st2(xp + q, p);
+        acc[0] = acc[0] + in.g.x * uu.x;
+        acc[1] = acc[1] + uu.x * uu.x;
+        acc[2] = acc[2] + p.x * p.x;
+        if (v2) {
+            acc[0] = acc[0] + in.g.y * uu.y;
+            acc[1] = acc[1] + uu.y * uu.y;
+            acc[2] = acc[2] + p.y * p.y;
+        }
+    }
+};
+
+// L-BFGS: S = xp − x, Y = g⁺ − g; pack {s·y, y·y}
+struct LbfgsStage {
+    static constexpr int TCLASS = CGO_T_LBFGS;
+    static constexpr int K = 2;
+    static constexpr int OCC = 2;
+    struct In { double2 xp, x, gp, g; };
+    const double2 *xp, *x, *gp, *g;
+    double2 *S, *Y;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.xp = cgo_ld2(xp + q); r.x = cgo_ld2(x + q); r.gp = cgo_ld2(gp + q); r.g = cgo_ld2(g + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 s, y;
+        s.x = in.xp.x - in.x.x; y.x = in.gp.x - in.g.x;
+        s.y = v2 ? in.xp.y - in.x.y : 0.0; y.y = v2 ? in.gp.y - in.g.y : 0.0;
+        cgo_st2(S + q, s); cgo_st2(Y + q, y);
+        acc[0] = acc[0] + s.x * y.x; acc[1] = acc[1] + y.x * y.x;
+        if (v2) { acc[0] = acc[0] + s.y * y.y; acc[1] = acc[1] + y.y * y.y; }
+    }
+};
+
+// Two-loop recursion steps.  Scalars produced by the previous kernel are read from device
+// memory (no host round trip inside the recursion).
+//  MODE 0: q = g;                              dot = S·q          (first step of loop 1)
+//  MODE 1: q = q − (ρp·dp) Yp;                 dot = S·q          (loop 1)
+//  MODE 2: q = q − (ρp·dp) Yp; q = γ q;        dot = Y·q          (end of loop 1, start of loop 2)
+//  MODE 3: q = q + Sp (αp − ρp·dp);            dot = Y·q          (loop 2)
+//  MODE 4: q = q + Sp (αp − ρp·dp); u = −q;    pack {g·u, u·u}    (end of loop 2)
+// with αp = ρp·(loop-1 dot of that pair) read from alpha_slot.
+template <int MODE>
+struct LbfgsStep {
+    static constexpr int TCLASS = CGO_T_LBFGS;
+    static constexpr int K = (MODE == 4) ? 2 : 1;
+    static constexpr int OCC = 2;
+    struct In { double2 q, a, b; };
+    double2 *q;             // in/out
+    const double2 *A;       // Yp (modes 1,2) or Sp (modes 3,4) or g (mode 0)
+    const double2 *B;       // vector dotted with the new q (modes 0-3) or g (mode 4)
+    double2 *uout;          // mode 4
+    const double *dprev;    // device scalar: previous kernel's dot
+    const double *alpha_dot;// device scalar: loop-1 dot of the pair applied in modes 3,4
+    double rho_prev, gamma;
+    double coef;
+    __device__ __forceinline__ void prologue() {
+        if (MODE == 1 || MODE == 2) coef = rho_prev * __ldcg(dprev);
+        if (MODE == 3 || MODE == 4) coef = rho_prev * __ldcg(alpha_dot) - rho_prev * __ldcg(dprev);
+    }
+    __device__ __forceinline__ In load(int64_t i) const {
+        In r;
+        if (MODE != 0) r.q = ld2rw(q + i);
+        r.a = cgo_ld2(A + i);
+        r.b = cgo_ld2(B + i);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t i, const In &in, double (&acc)[K], bool v2) const {
+        double2 qn;
+        if (MODE == 0) { qn = in.a; }
+        else if (MODE == 1 || MODE == 2) { qn.x = in.q.x - coef * in.a.x; qn.y = in.q.y - coef * in.a.y; }
+        else { qn.x = in.q.x + in.a.x * coef; qn.y = in.q.y + in.a.y * coef; }
+        if (MODE == 2) { qn.x = gamma * qn.x; qn.y = gamma * qn.y; }
+        if (!v2) qn.y = 0.0;
+        if (MODE == 4) {
+            double2 un; un.x = -qn.x; un.y = v2 ? -qn.y : 0.0;
+            cgo_st2(uout + i, un);
+            acc[0] = acc[0] + in.b.x * un.x; acc[1] = acc[1] + un.x * un.x;
+            if (v2) { acc[0] = acc[0] + in.b.y * un.y; acc[1] = acc[1] + un.y * un.y; }
+        } else {
+            cgo_st2(q + i, qn);
+            acc[0] = acc[0] + in.b.x * qn.x;
+            if (v2) acc[0] = acc[0] + in.b.y * qn.y;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ Rosenbrock objective
+static inline uint64_t h_mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+double cgo_host_u01(uint64_t seed, uint64_t i, uint64_t k) {
+    uint64_t h = h_mix64(seed + 0x9E3779B97F4A7C15ULL);
+    h = h_mix64(h ^ (i + 0x9E3779B97F4A7C15ULL));
+    h = h_mix64(h ^ (k + 0x632BE59BD9B4E019ULL));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct RosenObj : cgo_obj {
+    int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        RedArgs red = cgo_red_args(ctx);
+        if (fused) {
+            RosenTrial<true> op;
+            op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
+            op.xp = (double2 *)st->xp; op.gp = (double2 *)st->gp; op.a = a; op.beta = beta;
+            CGO_TRY(launch_blas1(ctx, op, st->n, red));
+        } else {
+            RosenTrial<false> op;
+            op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
+            op.xp = (double2 *)st->xp; op.gp = (double2 *)st->gp; op.a = a; op.beta = 0.0;
+            CGO_TRY(launch_blas1(ctx, op, st->n, red));
+        }
+        return cgo_finish_pack(ctx, 9, out);
+    }
+    // fused minimum: R x,g,u ; W (u,) xp, g⁺
+    double bytes_per_eval() const override { return 8.0 * 5.0 * (double)n_local; }
+    int default_x0(uint64_t seed, double perturb, double *x0) override {
+        for (int64_t i = 0; i < n_local; ++i) {
+            int64_t gi = offset + i;
+            double base = (gi % 2 == 0) ? -1.2 : 1.0;
+            x0[i] = perturb != 0.0 ? base + perturb * (2.0 * cgo_host_u01(seed, (uint64_t)gi, 0) - 1.0) : base;
+        }
+        return 0;
+    }
+};
+
+extern "C" int cgo_obj_rosenbrock_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out) {
+    CGO_CHECK(ctx && out, "NULL argument");
+    CGO_CHECK(n_global >= 2 && n_global % 2 == 0, "extended Rosenbrock needs an even n >= 2 (got %lld)", (long long)n_global);
+    RosenObj *o = new RosenObj();
+    o->ctx = ctx;
+    o->n_global = n_global;
+    int64_t lo, hi;
+    CGO_TRY(cgo_shard_range(n_global, ctx->nranks, ctx->rank, 2, &lo, &hi));
+    o->offset = lo;
+    o->n_local = hi - lo;
+    *out = o;
+    return 0;
+}
+extern "C" int cgo_obj_destroy(cgo_obj *o) {
+    delete o;
+    return 0;
+}
+extern "C" int cgo_obj_dims(cgo_obj *o, int64_t *nl, int64_t *ng, int64_t *off) {
+    CGO_CHECK(o != nullptr, "NULL objective");
+    if (nl) *nl = o->n_local;
+    if (ng) *ng = o->n_global;
+    if (off) *off = o->offset;
+    return 0;
+}
+extern "C" int cgo_obj_bytes_per_eval(cgo_obj *o, double *bytes) {
+    CGO_CHECK(o && bytes, "NULL argument");
+    *bytes = o->bytes_per_eval();
+    return 0;
+}
+extern "C" int cgo_obj_default_x0(cgo_obj *o, uint64_t seed, double perturb, double *x0) {
+    CGO_CHECK(o && x0, "NULL argument");
+    return o->default_x0(seed, perturb, x0);
+}
+
+// ------------------------------------------------------------------ solver state
+static int alloc_vec(cgo_state *st, double **base, double **ptr) {
+    size_t len = (size_t)(st->n + 2 * st->halo + 4);
+    CGO_CUDA(cudaMalloc(base, sizeof(double) * len));
+    CGO_CUDA(cudaMemsetAsync(*base, 0, sizeof(double) * len, st->ctx->stream));
+    *ptr = *base + st->halo;
+    return 0;
+}
+
+extern "C" int cgo_state_destroy(cgo_state *st) {
+    if (!st) return 0;
+    cudaSetDevice(st->ctx->device);
+    cudaStreamSynchronize(st->ctx->stream);
+    for (int i = 0; i < 5; ++i) cudaFree(st->base[i]);
+    for (auto p : st->S) cudaFree(p);
+    for (auto p : st->Y) cudaFree(p);
+    cudaFree(st->q);
+    delete st;
+    return 0;
+}
+
+extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, int32_t lbfgs_m,
+                                cgo_state **out_state, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(ctx && obj && x0 && out_state && out, "cgo_state_create: NULL argument");
+    CGO_CHECK(obj->ctx == ctx, "objective belongs to another ctx");
+    CGO_CHECK(lbfgs_m >= 0 && lbfgs_m <= CGO_LBFGS_MAX_M, "lbfgs_m=%d out of [0,%d]", lbfgs_m, CGO_LBFGS_MAX_M);
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    cgo_state *st = new cgo_state();
+    st->ctx = ctx; st->obj = obj; st->n = obj->n_local; st->halo = obj->halo;
+    // halo must keep 16-byte alignment of the local part
+    CGO_CHECK(st->halo % 2 == 0, "halo must be even");
+    double **ptrs[5] = {&st->x, &st->g, &st->u, &st->xp, &st->gp};
+    for (int i = 0; i < 5; ++i) {
+        int r = alloc_vec(st, &st->base[i], ptrs[i]);
+        if (r) { cgo_state_destroy(st); return r; }
+    }
+    st->m = lbfgs_m;
+    if (lbfgs_m > 0) {
+        size_t len = (size_t)(st->n + 4);
+        for (int k = 0; k < lbfgs_m; ++k) {
+            double *s = nullptr, *y = nullptr;
+            CGO_CUDA(cudaMalloc(&s, sizeof(double) * len));
+            st->S.push_back(s);
+            CGO_CUDA(cudaMalloc(&y, sizeof(double) * len));
+            st->Y.push_back(y);
+            CGO_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * len, ctx->stream));
+            CGO_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * len, ctx->stream));
+        }
+        st->rho.assign(lbfgs_m, 0.0);
+        CGO_CUDA(cudaMalloc(&st->q, sizeof(double) * len));
+        CGO_CUDA(cudaMemsetAsync(st->q, 0, sizeof(double) * len, ctx->stream));
+    }
+    // optim.jl:21 x = copy(x_initial); :25 f_x = fdf!(df_x, x): evaluate at x0 through the trial
+    // kernels with u = 0, a = 0 (xp = x0 + 0*0 = x0 exactly), then adopt (xp, g⁺) as (x, g).
+    CGO_CUDA(cudaMemcpyAsync(st->x, x0, sizeof(double) * (size_t)st->n, cudaMemcpyHostToDevice, ctx->stream));
+    int r = obj->eval_trial(st, 0.0, false, 0.0, out);
+    if (r) { cgo_state_destroy(st); return r; }
+    cgo_accept(st);
+    *out_state = st;
+    return 0;
+}
+
+extern "C" int cgo_accept(cgo_state *st) {
+    CGO_CHECK(st != nullptr, "NULL state");
+    std::swap(st->x, st->xp);
+    std::swap(st->g, st->gp);
+    std::swap(st->base[0], st->base[3]);
+    std::swap(st->base[1], st->base[4]);
+    return 0;
+}
+
+extern "C" int cgo_eval_trial(cgo_state *st, double a, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    return st->obj->eval_trial(st, a, false, 0.0, out);
+}
+extern "C" int cgo_eval_trial_fused_dir(cgo_state *st, double beta, double a, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    return st->obj->eval_trial(st, a, true, beta, out);
+}
+
+extern "C" int cgo_update_dir(cgo_state *st, double beta, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    DirUpdate<false> op;
+    op.g = (const double2 *)st->g; op.u = (double2 *)st->u; op.beta = beta;
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx)));
+    return cgo_finish_pack(st->ctx, 2, out);
+}
+extern "C" int cgo_reset_direction(cgo_state *st, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    DirUpdate<true> op;
+    op.g = (const double2 *)st->g; op.u = (double2 *)st->u; op.beta = 0.0;
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx)));
+    return cgo_finish_pack(st->ctx, 2, out);
+}
+extern "C" int cgo_beta_literal(cgo_state *st, double R, double m, double *beta_out) {
+    CGO_CHECK(st && beta_out, "NULL argument");
+    BetaLiteral op;
+    op.gp = (const double2 *)st->gp; op.g = (const double2 *)st->g; op.u = (const double2 *)st->u;
+    op.R = R; op.m = m;
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx)));
+    double tmp[CGO_PACK_LEN];
+    CGO_TRY(cgo_finish_pack(st->ctx, 1, tmp));
+    *beta_out = tmp[0];
+    return 0;
+}
+extern "C" int cgo_norm_sq_u_plus_g(cgo_state *st, double *outv) {
+    CGO_CHECK(st && outv, "NULL argument");
+    NormUPlusG op;
+    op.g = (const double2 *)st->g; op.u = (const double2 *)st->u;
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx)));
+    double tmp[CGO_PACK_LEN];
+    CGO_TRY(cgo_finish_pack(st->ctx, 1, tmp));
+    *outv = tmp[0];
+    return 0;
+}
+
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta, bool) {
+    // writes {g·u, u·u, xp·xp} to the reduction output (device pack slots 0..2)
+    if (fused) {
+        AxpyDir<true> op;
+        op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
+        op.xp = (double2 *)st->xp; op.a = a; op.beta = beta;
+        return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx));
+    }
+    AxpyDir<false> op;
+    op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
+    op.xp = (double2 *)st->xp; op.a = a; op.beta = 0.0;
+    return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx));
+}
+
+// ------------------------------------------------------------------ L-BFGS
+extern "C" int cgo_lbfgs_stage_pair(cgo_state *st, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    CGO_CHECK(st->m > 0, "state was created without an L-BFGS history (lbfgs_m = 0)");
+    int slot = (st->count == 0) ? 0 : (st->head + 1) % st->m;
+    LbfgsStage op;
+    op.xp = (const double2 *)st->xp; op.x = (const double2 *)st->x;
+    op.gp = (const double2 *)st->gp; op.g = (const double2 *)st->g;
+    op.S = (double2 *)st->S[slot]; op.Y = (double2 *)st->Y[slot];
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx)));
+    st->staged = slot;
+    return cgo_finish_pack(st->ctx, 2, out);
+}
+extern "C" int cgo_lbfgs_commit_pair(cgo_state *st, int32_t commit, double rho, double gamma) {
+    CGO_CHECK(st != nullptr, "NULL state");
+    CGO_CHECK(st->staged >= 0, "cgo_lbfgs_commit_pair without a staged pair");
+    if (commit) {
+        st->head = st->staged;
+        if (st->count < st->m) st->count++;
+        st->rho[st->staged] = rho;
+        st->gamma = gamma;
+    } else if (st->count == st->m) {
+        st->count--;     // the staged slot overwrote the oldest pair
+    }
+    st->staged = -1;
+    return 0;
+}
+
+// publish the dot of the kernel that just ran into d_scal[slot] (all ranks, rank order)
+__global__ void k_sum_ranks_to(const double *gathered, int nranks, double *dst) {
+    double s = gathered[0];
+    for (int r = 1; r < nranks; ++r) s = s + gathered[(size_t)r * CGO_PACK_LEN];
+    *dst = s;
+}
+static RedArgs red_to_slot(cgo_ctx *c, int slot) {
+    RedArgs r = cgo_red_args(c);
+    r.out = (c->nranks > 1) ? c->d_pack : c->d_scal + slot;
+    return r;
+}
+static int publish_slot(cgo_ctx *c, int slot) {
+    if (c->nranks > 1) {
+        CGO_TRY(cgo_allgather_bytes(c, c->d_pack, c->d_gather, sizeof(double) * CGO_PACK_LEN));
+        k_sum_ranks_to<<<1, 1, 0, c->stream>>>(c->d_gather, c->nranks, c->d_scal + slot);
+        c->launches++;
+    }
+    return 0;
+}
+
+extern "C" int cgo_lbfgs_update_dir(cgo_state *st, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    CGO_CHECK(st->m > 0, "state was created without an L-BFGS history (lbfgs_m = 0)");
+    cgo_ctx *c = st->ctx;
+    if (st->count == 0) return cgo_reset_direction(st, out);
+    const int cnt = st->count, m = st->m;
+    auto slot_of = [&](int k) { return ((st->head - k) % m + m) % m; };   // k = 0 newest
+    double2 *q = (double2 *)st->q;
+    // loop 1 (newest → oldest): dots land in d_scal[k]
+    for (int k = 0; k < cnt; ++k) {
+        int s = slot_of(k);
+        if (k == 0) {
+            LbfgsStep<0> op{};
+            op.q = q; op.A = (const double2 *)st->g; op.B = (const double2 *)st->S[s];
+            CGO_TRY(launch_blas1(c, op, st->n, red_to_slot(c, k)));
+        } else {
+            int sp = slot_of(k - 1);
+            LbfgsStep<1> op{};
+            op.q = q; op.A = (const double2 *)st->Y[sp]; op.B = (const double2 *)st->S[s];
+            op.dprev = c->d_scal + (k - 1); op.rho_prev = st->rho[sp];
+            CGO_TRY(launch_blas1(c, op, st->n, red_to_slot(c, k)));
+        }
+        CGO_TRY(publish_slot(c, k));
+    }
+    // end of loop 1 + scaling + first dot of loop 2 (oldest pair): dots of loop 2 in d_scal[64+k]
+    {
+        int sp = slot_of(cnt - 1);
+        LbfgsStep<2> op{};
+        op.q = q; op.A = (const double2 *)st->Y[sp]; op.B = (const double2 *)st->Y[sp];
+        op.dprev = c->d_scal + (cnt - 1); op.rho_prev = st->rho[sp]; op.gamma = st->gamma;
+        CGO_TRY(launch_blas1(c, op, st->n, red_to_slot(c, 64 + cnt - 1)));
+        CGO_TRY(publish_slot(c, 64 + cnt - 1));
+    }
+    // loop 2 (oldest → newest)
+    for (int k = cnt - 2; k >= 0; --k) {
+        int sp = slot_of(k + 1), s = slot_of(k);
+        LbfgsStep<3> op{};
+        op.q = q; op.A = (const double2 *)st->S[sp]; op.B = (const double2 *)st->Y[s];
+        op.dprev = c->d_scal + 64 + (k + 1); op.alpha_dot = c->d_scal + (k + 1); op.rho_prev = st->rho[sp];
+        CGO_TRY(launch_blas1(c, op, st->n, red_to_slot(c, 64 + k)));
+        CGO_TRY(publish_slot(c, 64 + k));
+    }
+    {
+        int sp = slot_of(0);
+        LbfgsStep<4> op{};
+        op.q = q; op.A = (const double2 *)st->S[sp]; op.B = (const double2 *)st->g; op.uout = (double2 *)st->u;
+        op.dprev = c->d_scal + 64; op.alpha_dot = c->d_scal; op.rho_prev = st->rho[sp];
+        CGO_TRY(launch_blas1(c, op, st->n, cgo_red_args(c)));
+    }
+    return cgo_finish_pack(c, 2, out);
+}
+
+// ------------------------------------------------------------------ downloads
+extern "C" int cgo_download(cgo_state *st, double *x_host, double *g_host) {
+    CGO_CHECK(st != nullptr, "NULL state");
+    cudaStream_t s = st->ctx->stream;
+    if (x_host) CGO_CUDA(cudaMemcpyAsync(x_host, st->x, sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToHost, s));
+    if (g_host) CGO_CUDA(cudaMemcpyAsync(g_host, st->g, sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToHost, s));
+    CGO_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int cgo_download_vector(cgo_state *st, int32_t which, double *host) {
+    CGO_CHECK(st && host, "NULL argument");
+    double *src[5] = {st->x, st->g, st->u, st->xp, st->gp};
+    CGO_CHECK(which >= 0 && which < 5, "which=%d out of range", which);
+    CGO_CUDA(cudaMemcpyAsync(host, src[which], sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToHost, st->ctx->stream));
+    CGO_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    return 0;
+}

@@ -1,0 +1,277 @@
+// context.cu — ctx lifetime, error channel, NCCL plumbing (dlopen'd), scalar-pack finish.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "internal.cuh"
+
+// ------------------------------------------------------------------ error channel
+static thread_local char g_err[1024] = "";
+void cgo_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *cgo_last_error(void) { return g_err; }
+extern "C" int cgo_version(void) { return 100; }
+
+// ------------------------------------------------------------------ NCCL via dlopen
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.handle) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    CGO_CHECK(h != nullptr, "dlopen(libnccl.so.2) failed: %s", dlerror());
+#define L(name)                                                         \
+    *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name);                  \
+    CGO_CHECK(g_nccl.name != nullptr, "dlsym(nccl" #name ") failed")
+    L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(AllGather); L(AllReduce); L(Send); L(Recv);
+    L(GroupStart); L(GroupEnd); L(GetErrorString);
+#undef L
+    g_nccl.handle = h;
+    return 0;
+}
+#define CGO_NCCL(call)                                                                          \
+    do {                                                                                        \
+        ncclResult_t r__ = (call);                                                              \
+        if (r__ != ncclSuccess) {                                                               \
+            cgo_set_error("%s failed: %s", #call, g_nccl.GetErrorString(r__));                  \
+            return 3;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------ ctx
+extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
+    CGO_CHECK(out != nullptr, "cgo_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cgo_set_error("cgo_ctx_create: no CUDA device (%s); libcgoptim has no CPU fallback",
+                      cudaGetErrorString(e));
+        return 1;
+    }
+    CGO_CHECK(device >= 0 && device < ndev, "cgo_ctx_create: device %d out of range [0,%d)", device, ndev);
+    CGO_CUDA(cudaSetDevice(device));
+    cgo_ctx *c = new cgo_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CGO_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        CGO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CGO_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * CGO_MAXK * CGO_GMAX));
+    CGO_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
+    CGO_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int) * 4, c->stream));
+    CGO_CUDA(cudaHostAlloc(&c->h_pack, sizeof(double) * CGO_PACK_LEN, cudaHostAllocMapped));
+    CGO_CUDA(cudaHostGetDevicePointer(&c->d_pack_map, c->h_pack, 0));
+    CGO_CUDA(cudaMalloc(&c->d_pack, sizeof(double) * CGO_PACK_LEN));
+    CGO_CUDA(cudaMalloc(&c->d_scal, sizeof(double) * CGO_NSCAL));
+    CGO_CUDA(cudaMemsetAsync(c->d_pack, 0, sizeof(double) * CGO_PACK_LEN, c->stream));
+    CGO_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double) * CGO_NSCAL, c->stream));
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" int cgo_ctx_destroy(cgo_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)c->comm);
+    cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFreeHost(c->h_pack);
+    cudaFree(c->d_pack); cudaFree(c->d_gather); cudaFree(c->d_scal);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto &t : c->pending) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+extern "C" int cgo_ctx_stream(cgo_ctx *c, void **s) {
+    CGO_CHECK(c && s, "cgo_ctx_stream: NULL argument");
+    *s = (void *)c->stream;
+    return 0;
+}
+extern "C" int cgo_ctx_set_reduction_ctas(cgo_ctx *c, int G) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CHECK(G >= 1 && G <= CGO_GMAX, "cgo_ctx_set_reduction_ctas: G=%d out of [1,%d]", G, CGO_GMAX);
+    c->G = G;
+    return 0;
+}
+extern "C" int cgo_ctx_sm_count(cgo_ctx *c, int *sms) {
+    CGO_CHECK(c && sms, "NULL argument");
+    *sms = c->sms;
+    return 0;
+}
+extern "C" int cgo_ctx_kernel_launches(cgo_ctx *c, int64_t *count) {
+    CGO_CHECK(c && count, "NULL argument");
+    *count = c->launches;
+    return 0;
+}
+
+extern "C" int cgo_comm_get_unique_id(void *id128) {
+    CGO_CHECK(id128 != nullptr, "NULL id");
+    CGO_TRY(nccl_load());
+    ncclUniqueId id;
+    CGO_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+extern "C" int cgo_ctx_comm_init(cgo_ctx *c, int nranks, int rank, const void *id128) {
+    CGO_CHECK(c && id128, "NULL argument");
+    CGO_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / %d", rank, nranks);
+    CGO_CUDA(cudaSetDevice(c->device));
+    c->nranks = nranks;
+    c->rank = rank;
+    if (nranks == 1) return 0;
+    CGO_TRY(nccl_load());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    CGO_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->comm = (void *)comm;
+    c->nccl = &g_nccl;
+    CGO_CUDA(cudaMalloc(&c->d_gather, sizeof(double) * CGO_PACK_LEN * nranks));
+    return 0;
+}
+
+extern "C" int cgo_shard_range(int64_t n, int nranks, int rank, int64_t align, int64_t *lo, int64_t *hi) {
+    CGO_CHECK(lo && hi && nranks >= 1 && rank >= 0 && rank < nranks && align >= 1, "cgo_shard_range: bad arguments");
+    int64_t units = n / align;
+    *lo = (units * rank / nranks) * align;
+    *hi = (rank == nranks - 1) ? n : (units * (rank + 1) / nranks) * align;
+    return 0;
+}
+
+int cgo_allgather_bytes(cgo_ctx *c, const void *send, void *recv, size_t bytes) {
+    if (c->nranks == 1) {
+        CGO_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    CGO_NCCL(g_nccl.AllGather(send, recv, bytes, ncclInt8, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+
+// ring halo exchange: my head goes to the previous rank (its right halo), my tail to the next
+// rank (its left halo)
+int cgo_sendrecv_ring(cgo_ctx *c, const double *send_to_prev, double *recv_from_next,
+                      const double *send_to_next, double *recv_from_prev, int64_t count) {
+    if (count <= 0) return 0;
+    if (c->nranks == 1) {
+        CGO_CUDA(cudaMemcpyAsync(recv_from_next, send_to_prev, sizeof(double) * count, cudaMemcpyDeviceToDevice, c->stream));
+        CGO_CUDA(cudaMemcpyAsync(recv_from_prev, send_to_next, sizeof(double) * count, cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    int prev = (c->rank + c->nranks - 1) % c->nranks, next = (c->rank + 1) % c->nranks;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    CGO_NCCL(g_nccl.GroupStart());
+    CGO_NCCL(g_nccl.Send(send_to_prev, (size_t)count, ncclFloat64, prev, comm, c->stream));
+    CGO_NCCL(g_nccl.Recv(recv_from_next, (size_t)count, ncclFloat64, next, comm, c->stream));
+    CGO_NCCL(g_nccl.Send(send_to_next, (size_t)count, ncclFloat64, next, comm, c->stream));
+    CGO_NCCL(g_nccl.Recv(recv_from_prev, (size_t)count, ncclFloat64, prev, comm, c->stream));
+    CGO_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-launch timing
+static cudaEvent_t ev_get(cgo_ctx *c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void cgo_timer_begin(cgo_ctx *c, int cls) {
+    if (!c->timing) return;
+    CgoPendingTimer t;
+    t.cls = cls; t.e0 = ev_get(c); t.e1 = ev_get(c);
+    cudaEventRecord(t.e0, c->stream);
+    c->pending.push_back(t);
+}
+void cgo_timer_end(cgo_ctx *c) {
+    if (!c->timing || c->pending.empty()) return;
+    cudaEventRecord(c->pending.back().e1, c->stream);
+}
+void cgo_timer_collect(cgo_ctx *c) {
+    for (auto &t : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) { c->t_ms[t.cls] += ms; c->t_cnt[t.cls]++; }
+        c->ev_pool.push_back(t.e0); c->ev_pool.push_back(t.e1);
+    }
+    c->pending.clear();
+}
+extern "C" int cgo_ctx_timing(cgo_ctx *c, int enable) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    cgo_timer_collect(c);
+    c->timing = enable != 0;
+    return 0;
+}
+extern "C" int cgo_ctx_timing_read(cgo_ctx *c, double *ms, int64_t *counts, int reset) {
+    CGO_CHECK(c && ms && counts, "NULL argument");
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    cgo_timer_collect(c);
+    for (int i = 0; i < CGO_T_N; ++i) { ms[i] = c->t_ms[i]; counts[i] = c->t_cnt[i]; }
+    if (reset) for (int i = 0; i < CGO_T_N; ++i) { c->t_ms[i] = 0; c->t_cnt[i] = 0; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ scalar pack finish
+RedArgs cgo_red_args(cgo_ctx *c) {
+    RedArgs r;
+    r.partial = c->d_partial;
+    r.ticket = c->d_ticket;
+    r.out = (c->nranks > 1) ? c->d_pack : c->d_pack_map;
+    r.G = c->G;
+    return r;
+}
+
+// shard results are added in rank order on every rank (canonical order, last level)
+__global__ void k_sum_ranks(const double *gathered, int nranks, int K, double *out) {
+    int k = threadIdx.x;
+    if (k < K) {
+        double s = gathered[k];
+        for (int r = 1; r < nranks; ++r) s = s + gathered[(size_t)r * CGO_PACK_LEN + k];
+        out[k] = s;
+    }
+    __threadfence_system();
+}
+
+int cgo_finish_pack(cgo_ctx *c, int K, double *out_host) {
+    if (c->nranks > 1) {
+        CGO_NCCL(g_nccl.AllGather(c->d_pack, c->d_gather, CGO_PACK_LEN, ncclFloat64, (ncclComm_t)c->comm, c->stream));
+        k_sum_ranks<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, K, c->d_pack_map);
+        c->launches++;
+    }
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->timing) cgo_timer_collect(c);
+    for (int k = 0; k < K; ++k) out_host[k] = c->h_pack[k];
+    return 0;
+}
+
+extern "C" int cgo_ctx_barrier(cgo_ctx *c) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    if (c->nranks > 1) {
+        CGO_NCCL(g_nccl.AllReduce(c->d_scal + CGO_NSCAL - 1, c->d_scal + CGO_NSCAL - 1, 1, ncclFloat64, ncclSum, (ncclComm_t)c->comm, c->stream));
+    }
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,126 @@
+// internal.cuh — shared declarations of libcgoptim.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cgoptim.h"
+
+// ------------------------------------------------------------------ errors
+void cgo_set_error(const char *fmt, ...);
+#define CGO_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            cgo_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,    \
+                          __LINE__);                                                            \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+#define CGO_CHECK(cond, ...)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            cgo_set_error(__VA_ARGS__);                                                         \
+            return 2;                                                                           \
+        }                                                                                       \
+    } while (0)
+#define CGO_TRY(call)                                                                           \
+    do {                                                                                        \
+        int r__ = (call);                                                                       \
+        if (r__) return r__;                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------ canonical reduction
+constexpr int CGO_B = 256;        // lanes per (virtual) CTA
+constexpr int CGO_NW = CGO_B / 32;
+constexpr int CGO_U_VEC = 4;      // double2 loads per lane per tile, BLAS-1 kernels (V = 2)
+constexpr int CGO_MAXK = 12;      // widest pack any kernel reduces
+
+struct RedArgs {
+    double *partial;        // [K][G] CTA partials
+    unsigned int *ticket;   // arrival counter, self-resetting
+    double *out;            // K results: mapped pinned host memory (1 rank) or device (R ranks)
+    int G;                  // virtual CTAs of the canonical order
+};
+
+// ------------------------------------------------------------------ context
+struct NcclApi;
+// kernel classes for the optional per-launch CUDA-event timing (bench.py roofline)
+enum { CGO_T_TRIAL = 0, CGO_T_DIR = 1, CGO_T_AXPY = 2, CGO_T_SPMV = 3, CGO_T_SPMVT = 4,
+       CGO_T_LBFGS = 5, CGO_T_OTHER = 6, CGO_T_BATCHED = 7, CGO_T_N = 8 };
+struct CgoPendingTimer { int cls; cudaEvent_t e0, e1; };
+struct cgo_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int G = 1184;
+    int64_t launches = 0;
+    // reduction scratch
+    double *d_partial = nullptr;     // CGO_MAXK * Gmax
+    unsigned int *d_ticket = nullptr;
+    double *h_pack = nullptr;        // pinned + mapped, CGO_PACK_LEN
+    double *d_pack_map = nullptr;    // device alias of h_pack
+    double *d_pack = nullptr;        // device pack (multi-rank)
+    double *d_gather = nullptr;      // nranks * CGO_PACK_LEN
+    double *d_scal = nullptr;        // device scalars for chained kernels (L-BFGS dots)
+    // optional timing
+    bool timing = false;
+    std::vector<CgoPendingTimer> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double t_ms[CGO_T_N] = {0};
+    int64_t t_cnt[CGO_T_N] = {0};
+    // communicator
+    int nranks = 1, rank = 0;
+    void *comm = nullptr;            // ncclComm_t
+    NcclApi *nccl = nullptr;
+};
+constexpr int CGO_GMAX = 8192;
+constexpr int CGO_NSCAL = 256;     // device scalar slots (L-BFGS dots), last one reserved
+constexpr int CGO_LBFGS_MAX_M = 64;
+
+// launch the pack finalisation for the current kernel sequence: after the producing kernel
+// wrote K sums to ctx->red_out(), make them visible on the host in out[0..K).
+RedArgs cgo_red_args(cgo_ctx *ctx);
+void cgo_timer_begin(cgo_ctx *ctx, int cls);   // records an event on the ctx stream (if enabled)
+void cgo_timer_end(cgo_ctx *ctx);
+void cgo_timer_collect(cgo_ctx *ctx);          // after a stream sync: fold pending timers
+int cgo_finish_pack(cgo_ctx *ctx, int K, double *out_host);
+int cgo_allgather_bytes(cgo_ctx *ctx, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
+int cgo_sendrecv_ring(cgo_ctx *ctx, const double *send_to_prev, double *recv_from_next,
+                      const double *send_to_next, double *recv_from_prev, int64_t count);
+
+// ------------------------------------------------------------------ objective interface
+struct cgo_state;
+struct cgo_obj {
+    cgo_ctx *ctx = nullptr;
+    int64_t n_global = 0, n_local = 0, offset = 0;
+    int64_t halo = 0;                 // elements of padding each side of every state vector
+    virtual ~cgo_obj() {}
+    // xp = x + a u (optionally u = −g + β u first), g⁺ = ∇f(xp), fills the device pack and
+    // finishes it into out_host.
+    virtual int eval_trial(cgo_state *st, double a, bool fused_dir, double beta,
+                           double *out_host) = 0;
+    virtual double bytes_per_eval() const = 0;
+    virtual int default_x0(uint64_t seed, double perturb, double *x0_host) = 0;
+};
+
+struct cgo_state {
+    cgo_ctx *ctx = nullptr;
+    cgo_obj *obj = nullptr;
+    int64_t n = 0;                    // local length
+    int64_t halo = 0;
+    double *base[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // allocations
+    double *x = nullptr, *g = nullptr, *u = nullptr, *xp = nullptr, *gp = nullptr;  // base + halo
+    // L-BFGS history
+    int m = 0, count = 0, head = 0, staged = -1;
+    std::vector<double *> S, Y;
+    std::vector<double> rho;
+    double gamma = 1.0;
+    double *q = nullptr;
+};
+
+// BLAS-1 kernels shared by objectives (blas1.cu)
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, bool want_ww);

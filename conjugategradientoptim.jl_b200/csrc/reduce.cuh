@@ -1,0 +1,82 @@
+// reduce.cuh — the canonical, deterministic reduction (spec: include/cgoptim.h).
+//
+// Replaces every LinearAlgebra.dot / norm call site of the reference (SURVEY.md §2 last row:
+// src/cg_utils.jl:20; src/engine/optim.jl:26,107; src/cg_flavours.jl:65-67,73,76,98,102,105,
+// 140-141,145,166-167; src/linesearch/nocedal.jl:56; wolfe.jl:40,123,240; geometric.jl:43,52).
+// Warp-shuffle butterfly + fixed-order CTA combine + last-block finish: no atomics on data,
+// run-to-run bitwise reproducible, independent of the physical grid.
+#pragma once
+#include "internal.cuh"
+
+// Combine the CGO_B lanes of a CTA.  Result valid in thread 0 (acc[] of thread 0).
+template <int K>
+__device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* K*CGO_NW */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[k * CGO_NW + warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = sm[k * CGO_NW];
+#pragma unroll
+            for (int w = 1; w < CGO_NW; ++w) s = s + sm[k * CGO_NW + w];
+            acc[k] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// Thread 0 of virtual CTA `vcta` publishes its K partials.
+template <int K>
+__device__ __forceinline__ void cgo_publish(const RedArgs &red, int vcta, const double (&acc)[K]) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) __stcg(&red.partial[(size_t)k * red.G + vcta], acc[k]);
+    }
+}
+
+// Called by every physical CTA once all its virtual CTAs are published.  The last CTA to arrive
+// combines the `nact` partials in canonical order and writes red.out[0..K).
+template <int K>
+__device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, double *sm) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(red.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int c = threadIdx.x; c < nact; c += CGO_B) s = s + __ldcg(&red.partial[(size_t)k * red.G + c]);
+        acc[k] = s;
+    }
+    cgo_cta_combine<K>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red.out[k] = acc[k];
+        *red.ticket = 0u;
+        __threadfence_system();
+    }
+}
+
+// 128-bit streaming loads / stores (inputs are read once per kernel: keep them out of L1)
+__device__ __forceinline__ double2 cgo_ld2(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void cgo_st2(double2 *p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}

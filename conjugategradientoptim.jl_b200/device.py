@@ -1,0 +1,392 @@
+"""Device context, objective handles and the device-resident LineSearchContainer.
+
+The reference keeps `xp, df_xp, x, u` (src/types.jl:84-100) and `x, df_x`
+(src/engine/optim.jl:20-21) as host Vectors.  Here they live in HBM behind a `cgo_state`; the
+host sees them as `DeviceVector` tokens so that the engine and the line searches keep the
+reference's call shapes (`evalϕdϕ_(xp, df_xp, fdf_, a, x, u)`, `dot(df_x, u)`,
+`getβ(β_config, g_next, g, u)`, `updatedir_(u, df_x, β)`).
+
+No CPU fallback: everything here goes through libcgoptim.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import (D_GU, D_UU, P_DPHI, P_GPG, P_GPGP, P_PHI, P_UG, P_UU, P_UY, P_YGP, P_YY,
+                    PACK_LEN, check, dptr, lib)
+
+f64 = np.float64
+
+
+class Context:
+    """One GPU, one stream, optionally one rank of an NCCL communicator (`cgo_ctx`)."""
+
+    def __init__(self, device: int = 0, stream_ptr: int = 0, reduction_ctas: Optional[int] = None):
+        h = C.c_void_p()
+        check(lib().cgo_ctx_create(device, C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.nranks, self.rank = 1, 0
+        if reduction_ctas is not None:
+            self.set_reduction_ctas(reduction_ctas)
+
+    def set_reduction_ctas(self, G: int):
+        check(lib().cgo_ctx_set_reduction_ctas(self.h, G))
+
+    @property
+    def stream_ptr(self) -> int:
+        s = C.c_void_p()
+        check(lib().cgo_ctx_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def sm_count(self) -> int:
+        v = C.c_int()
+        check(lib().cgo_ctx_sm_count(self.h, C.byref(v)))
+        return v.value
+
+    @property
+    def kernel_launches(self) -> int:
+        v = C.c_int64()
+        check(lib().cgo_ctx_kernel_launches(self.h, C.byref(v)))
+        return v.value
+
+    KERNEL_CLASSES = ("trial", "direction", "axpy", "spmv", "spmvT", "lbfgs", "other", "batched")
+
+    def timing(self, enable: bool):
+        check(lib().cgo_ctx_timing(self.h, int(enable)))
+
+    def timing_read(self, reset: bool = True):
+        """{class: (total_ms, launches)} measured with CUDA events on the ctx stream."""
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.int64)
+        check(lib().cgo_ctx_timing_read(self.h, dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64)), int(reset)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    # -- multi-GPU: one process per GPU; the 128-byte id travels over the host's own channel
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().cgo_comm_get_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib().cgo_ctx_comm_init(self.h, nranks, rank, buf))
+        self.nranks, self.rank = nranks, rank
+
+    def comm_init_torch(self):
+        """Bootstrap the communicator through an initialised torch.distributed group."""
+        import torch.distributed as dist
+        nranks, rank = dist.get_world_size(), dist.get_rank()
+        ids = [Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.comm_init(nranks, rank, ids[0])
+
+    def barrier(self):
+        check(lib().cgo_ctx_barrier(self.h))
+
+    def close(self):
+        if self.h:
+            lib().cgo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def shard_range(n: int, nranks: int, rank: int, align: int = 2):
+    lo, hi = C.c_int64(), C.c_int64()
+    check(lib().cgo_shard_range(n, nranks, rank, align, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+# ---------------------------------------------------------------------------------- objectives
+class DeviceObjective:
+    """Device-resident replacement of the user callback `fdf!(g, x) -> f`."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx, self.h = ctx, handle
+        nl, ng, off = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().cgo_obj_dims(self.h, C.byref(nl), C.byref(ng), C.byref(off)))
+        self.n_local, self.n_global, self.offset = nl.value, ng.value, off.value
+
+    @property
+    def bytes_per_eval(self) -> float:
+        v = C.c_double()
+        check(lib().cgo_obj_bytes_per_eval(self.h, C.byref(v)))
+        return v.value
+
+    def default_x0(self, seed: int = 24, perturb: float = 0.0) -> np.ndarray:
+        x0 = np.empty(self.n_local)
+        check(lib().cgo_obj_default_x0(self.h, seed, perturb, dptr(x0)))
+        return x0
+
+    def make_workspace(self, x_initial, lbfgs_m: int = 0, fuse_direction: bool = True,
+                       beta_form: str = "fused"):
+        return DeviceLineSearchContainer(self, x_initial, lbfgs_m, fuse_direction, beta_form)
+
+    # CSR test hooks
+    def csr(self, transposed=False):
+        nr, nnz = C.c_int64(), C.c_int64()
+        check(lib().cgo_obj_csr_nnz(self.h, int(transposed), C.byref(nr), C.byref(nnz)))
+        rp = np.empty(nr.value + 1, dtype=np.int64)
+        ci = np.empty(nnz.value, dtype=np.int32)
+        va = np.empty(nnz.value)
+        b = np.empty(nr.value)
+        check(lib().cgo_obj_csr_download(self.h, int(transposed), rp.ctypes.data, ci.ctypes.data,
+                                         va.ctypes.data, b.ctypes.data))
+        return rp, ci, va, b
+
+    def spmv(self, x, transposed=False):
+        nr, nnz = C.c_int64(), C.c_int64()
+        check(lib().cgo_obj_csr_nnz(self.h, int(transposed), C.byref(nr), C.byref(nnz)))
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(nr.value)
+        check(lib().cgo_obj_spmv(self.h, int(transposed), dptr(x), dptr(y)))
+        return y
+
+    def close(self):
+        if self.h:
+            lib().cgo_obj_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def RosenbrockGPU(n: int, ctx: Optional[Context] = None) -> DeviceObjective:
+    """Extended Rosenbrock (pairs), SURVEY.md §8d cfg 1/2/5."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    check(lib().cgo_obj_rosenbrock_create(ctx.h, n, C.byref(h)))
+    return DeviceObjective(ctx, h)
+
+
+def SparseLSGPU(n: int, nnz_per_row: int = 10, W: Optional[int] = None, seed: int = 24,
+                coh_log2: int = 0, ctx: Optional[Context] = None) -> DeviceObjective:
+    """½‖Ax − b‖² with the synthetic banded-random CSR of SURVEY.md §8d cfg 3."""
+    ctx = ctx or default_context()
+    if W is None:
+        W = min(1 << 20, (n - 1) // 2)
+    h = C.c_void_p()
+    check(lib().cgo_obj_sparse_ls_create_synthetic(ctx.h, n, nnz_per_row, W, seed, coh_log2, C.byref(h)))
+    return DeviceObjective(ctx, h)
+
+
+def SparseLSGPU_from_csr(nrows, ncols, rowptr, col, val, b, ctx: Optional[Context] = None) -> DeviceObjective:
+    ctx = ctx or default_context()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    h = C.c_void_p()
+    check(lib().cgo_obj_sparse_ls_create_csr(ctx.h, nrows, ncols, rowptr.ctypes.data, col.ctypes.data,
+                                             val.ctypes.data, b.ctypes.data, C.byref(h)))
+    return DeviceObjective(ctx, h)
+
+
+def LogRegGPU(nsamples: int, nfeat: int, nnz_per_row: int = 20, seed: int = 24, lam: float = 1e-6,
+              ctx: Optional[Context] = None) -> DeviceObjective:
+    """CSR logistic regression, SURVEY.md §8d cfg 4."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    check(lib().cgo_obj_logreg_create_synthetic(ctx.h, nsamples, nfeat, nnz_per_row, seed, lam, C.byref(h)))
+    return DeviceObjective(ctx, h)
+
+
+# ---------------------------------------------------------------------------------- vectors
+class DeviceVector:
+    """Token for one of the device-resident vectors of a LineSearchContainer."""
+    __slots__ = ("ws", "name")
+
+    def __init__(self, ws, name: str):
+        self.ws, self.name = ws, name
+
+    def __repr__(self):
+        return f"<DeviceVector {self.name} n={self.ws.n}>"
+
+
+def dot(a: DeviceVector, b: DeviceVector):
+    """LinearAlgebra.dot on device vectors.  Only the pairs the hot path needs exist:
+    dot(df_x, u) (nocedal.jl:56, wolfe.jl:40, geometric.jl:43) and dot(u, u) (wolfe.jl:240,
+    geometric.jl:52); both were produced by the kernel that last wrote u."""
+    names = {a.name, b.name}
+    if names == {"df_x", "u"}:
+        return a.ws.dot_g_u()
+    if names == {"u"}:
+        return a.ws.dot_u_u()
+    raise NotImplementedError(f"dot({a.name}, {b.name}) is not on the hot path")
+
+
+class DeviceLineSearchContainer:
+    """LineSearchContainer (types.jl:84-100) + x, df_x of optim.jl:20-21, resident in HBM.
+
+    Construction performs optim.jl:20-26: copies x_initial to the device, evaluates
+    f_x = fdf!(df_x, x) and ‖df_x‖.
+    """
+
+    def __init__(self, objective: DeviceObjective, x_initial, lbfgs_m=0, fuse_direction=True,
+                 beta_form="fused"):
+        assert beta_form in ("fused", "literal")
+        x0 = np.ascontiguousarray(x_initial, dtype=np.float64)
+        if x0.shape != (objective.n_local,):
+            raise ValueError(f"x_initial has shape {x0.shape}, objective shard has n={objective.n_local}")
+        self.objective = objective
+        self.n = objective.n_local
+        self.fuse_direction = fuse_direction
+        self.beta_form = beta_form
+        self._buf = np.zeros(PACK_LEN)
+        self.h = C.c_void_p()
+        check(lib().cgo_state_create(objective.ctx.h, objective.h, dptr(x0), lbfgs_m, C.byref(self.h), dptr(self._buf)))
+        self.f_x0 = f64(self._buf[P_PHI])
+        self.norm_df_x0 = np.sqrt(f64(self._buf[P_GPGP]))
+        self.pack = self._buf.copy()          # last trial pack
+        self.dpack = np.zeros(2)              # last direction pack {g·u, u·u}
+        self._pending_beta = None             # lazily fused updatedir!
+        self._hint = None
+        self._cached = None                   # (a, pack) of a speculative first trial
+        self.fdf_evals = 1
+        self.xp, self.df_xp = DeviceVector(self, "xp"), DeviceVector(self, "df_xp")
+        self.x, self.u = DeviceVector(self, "x"), DeviceVector(self, "u")
+        self.df_x = DeviceVector(self, "df_x")
+
+    # -- direction -------------------------------------------------------------------
+    def reset_direction(self):
+        """u = −df_x (cg_flavours.jl:28, wolfe.jl:129)."""
+        self._pending_beta = None
+        self._cached = None
+        check(lib().cgo_reset_direction(self.h, dptr(self._buf)))
+        self.dpack = self._buf[:2].copy()
+
+    def update_dir(self, β):
+        """updatedir! (cg_flavours.jl:2-15).  With fuse_direction the kernel is deferred and
+        fused into the first trial of the next line search."""
+        self._cached = None
+        if self.fuse_direction:
+            self._pending_beta = float(β)
+        else:
+            check(lib().cgo_update_dir(self.h, float(β), dptr(self._buf)))
+            self.dpack = self._buf[:2].copy()
+
+    def hint_first_trial(self, a):
+        """The step the caller will evaluate first (lets the pending direction update ride on it)."""
+        self._hint = float(a)
+
+    def _materialize_direction(self):
+        if self._pending_beta is None:
+            return
+        β, self._pending_beta = self._pending_beta, None
+        if self._hint is not None and np.isfinite(self._hint):
+            a = self._hint
+            check(lib().cgo_eval_trial_fused_dir(self.h, β, a, dptr(self._buf)))
+            pk = self._buf.copy()
+            self._cached = (a, pk)
+            self.dpack = np.array([pk[P_UG], pk[P_UU]])
+        else:
+            check(lib().cgo_update_dir(self.h, β, dptr(self._buf)))
+            self.dpack = self._buf[:2].copy()
+        self._hint = None
+
+    def dot_g_u(self):
+        self._materialize_direction()
+        return f64(self.dpack[D_GU])
+
+    def dot_u_u(self):
+        self._materialize_direction()
+        return f64(self.dpack[D_UU])
+
+    def norm_u_plus_g(self):
+        """norm(u + df_x) (wolfe.jl:123)"""
+        self._materialize_direction()
+        v = C.c_double()
+        check(lib().cgo_norm_sq_u_plus_g(self.h, C.byref(v)))
+        return np.sqrt(f64(v.value))
+
+    # -- trial point -----------------------------------------------------------------
+    def eval_trial(self, a):
+        """evalϕdϕ! (cg_utils.jl:3-22): returns (ϕ, dϕ); the full pack stays in self.pack."""
+        self._materialize_direction()
+        a = float(a)
+        if self._cached is not None and self._cached[0] == a:
+            self.pack = self._cached[1]
+            self._cached = None
+        else:
+            self._cached = None
+            check(lib().cgo_eval_trial(self.h, a, dptr(self._buf)))
+            self.pack = self._buf.copy()
+        self.fdf_evals += 1
+        return f64(self.pack[P_PHI]), f64(self.pack[P_DPHI])
+
+    def norm_df_xp(self):
+        """norm(info.df_xp) (optim.jl:107)"""
+        return np.sqrt(f64(self.pack[P_GPGP]))
+
+    def beta_literal(self, R, m):
+        v = C.c_double()
+        check(lib().cgo_beta_literal(self.h, float(R), float(m), C.byref(v)))
+        return f64(v.value)
+
+    def accept(self):
+        """x[:] = info.xp; df_x[:] = info.df_xp; info.x[:] = x  (optim.jl:136-140): pointer swaps."""
+        self._cached = None
+        check(lib().cgo_accept(self.h))
+
+    # -- L-BFGS ----------------------------------------------------------------------
+    def lbfgs_stage_pair(self):
+        check(lib().cgo_lbfgs_stage_pair(self.h, dptr(self._buf)))
+        return f64(self._buf[0]), f64(self._buf[1])
+
+    def lbfgs_commit_pair(self, commit: bool, rho=0.0, gamma=1.0):
+        check(lib().cgo_lbfgs_commit_pair(self.h, int(commit), float(rho), float(gamma)))
+
+    def lbfgs_update_dir(self):
+        self._cached = None
+        self._pending_beta = None
+        check(lib().cgo_lbfgs_update_dir(self.h, dptr(self._buf)))
+        self.dpack = self._buf[:2].copy()
+
+    # -- results ---------------------------------------------------------------------
+    def download(self):
+        x, g = np.empty(self.n), np.empty(self.n)
+        check(lib().cgo_download(self.h, dptr(x), dptr(g)))
+        return x, g
+
+    def download_vector(self, name: str):
+        which = {"x": 0, "df_x": 1, "u": 2, "xp": 3, "df_xp": 4}[name]
+        if name == "u":
+            self._materialize_direction()
+        v = np.empty(self.n)
+        check(lib().cgo_download_vector(self.h, which, dptr(v)))
+        return v
+
+    def close(self):
+        if self.h:
+            lib().cgo_state_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -145,6 +145,7 @@ static double sum_term(const void *c, int64_t i) { return ((const double *)c)[i]
  * row-per-lane (CSR) kernels use V=1, U=1.  g_site_V/U select the mapping of the kernel that
  * computes the reduction at the current call site (see DESIGN.md "reduction sites"). */
 static int g_site_V = 2, g_site_U = 4;
+void orc_set_site(int V, int U) { g_site_V = V; g_site_U = U; }
 static double dot_cgo(const double *a, const double *b, int64_t n) {
     dot_ctx d = {a, b};
     return cgo_reduce(dot_term, &d, n, g_site_V, g_site_U, 2);
@@ -365,6 +366,8 @@ orc_objective *orc_obj_rosenbrock(int64_t n) { return (n % 2) ? NULL : obj_new(n
 orc_objective *orc_obj_rosenbrock_chained(int64_t n) { return obj_new(n, rosen_chained_fdf); }
 orc_objective *orc_obj_quartic_barrier(int64_t n) { return obj_new(n, barrier_fdf); }
 int64_t orc_obj_dim(const orc_objective *o) { return o->n; }
+void orc_obj_set_sum_mode(orc_objective *o, int mode, int threads) { o->sum_mode = mode; if (threads > 0) o->threads = threads; }
+void orc_obj_trial_site(const orc_objective *o, int *V, int *U) { *V = o->trial_V; *U = o->trial_U; }
 
 /* stable counting-sort transpose: rows of Aᵀ come out sorted by source row */
 static void build_transpose(orc_objective *o) {

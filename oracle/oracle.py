@@ -94,6 +94,9 @@ def lib():
     L.orc_sum_cgo.restype = C.c_double
     L.orc_sum_cgo.argtypes = [dp, C.c_int64, C.c_int, C.c_int64]
     L.orc_set_cgo_order.argtypes = [C.c_int, C.c_int]
+    L.orc_obj_set_sum_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.orc_obj_trial_site.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_set_site.argtypes = [C.c_int, C.c_int]
     L.orc_spmv.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.orc_hash_u01.restype = C.c_double
     L.orc_hash_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
@@ -194,6 +197,14 @@ class Objective:
         return Objective(lib().orc_obj_logreg_synth(nsamples, nfeat, nnz_per_row, seed, lam, threads))
 
     # primitives --------------------------------------------------------------------
+    def set_sum_mode(self, sum_mode="seq", threads=0):
+        lib().orc_obj_set_sum_mode(self.h, SUM_MODES[sum_mode], threads)
+
+    def trial_site(self):
+        v, u = C.c_int(), C.c_int()
+        lib().orc_obj_trial_site(self.h, C.byref(v), C.byref(u))
+        return v.value, u.value
+
     def fdf(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         g = np.empty(self.n)
@@ -238,6 +249,10 @@ def set_cgo_order(G=1184, shards=1):
 def sum_cgo(a, U=4, align=1):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return lib().orc_sum_cgo(_dp(a), a.size, U, align)
+
+
+def set_site(V=2, U=4):
+    lib().orc_set_site(V, U)
 
 
 def hash_u01(seed, i, k):

@@ -1,0 +1,163 @@
+"""GPU parity tests (through the C ABI) of the fused BLAS-1 chain on extended Rosenbrock.
+
+Bar: BIT-EXACT against the oracle in canonical-order mode (all arithmetic is IEEE +,−,×,÷,√ with
+FMA contraction off on both sides), which implies north_star's gates (f, ‖g‖ within 1e-10 over
+50 iterations, identical accept/reject decisions, iteration count ±2) with room to spare.
+"""
+import numpy as np
+import pytest
+
+import cgoptim_b200 as cg
+from oracle import oracle as O
+
+from helpers import FLAVOURS, LINESEARCHES, assert_same_run, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n", [2, 4, 10, 2048, 2050, 4096 + 6, 100_000, 1_000_002])
+@pytest.mark.parametrize("G", [1184, 3])
+def test_trial_pack_bit_exact(ctx, n, G):
+    """cgo_eval_trial pack == oracle fdf + canonical-order dots (evalϕdϕ!, cg_utils.jl:3-22)."""
+    ctx.set_reduction_ctas(G)
+    O.set_cgo_order(G, 1)
+    try:
+        obj = cg.RosenbrockGPU(n, ctx)
+        x0 = obj.default_x0(24, 0.1)
+        assert np.array_equal(x0, O.rosenbrock_x0(n, 24, 0.1))
+        ws = obj.make_workspace(x0, fuse_direction=False)
+        oo = O.Objective.rosenbrock(n)
+        oo.set_sum_mode("cgo")
+        f0, g0 = oo.fdf(x0)
+        assert ws.f_x0 == f0
+        assert np.array_equal(ws.download()[1], g0)
+        ws.reset_direction()
+        u = -g0
+        assert ws.dot_g_u() == O.dot(g0, u, "cgo") and ws.dot_u_u() == O.dot(u, u, "cgo")
+        a = 1e-3
+        phi, dphi = ws.eval_trial(a)
+        xp = x0 + a * u
+        f1, g1 = oo.fdf(xp)
+        y = g1 - g0
+        P = ws.pack
+        assert np.array_equal(ws.download_vector("xp"), xp)
+        assert np.array_equal(ws.download_vector("df_xp"), g1)
+        expect = [f1, O.dot(g1, u, "cgo"), O.dot(g1, g1, "cgo"), O.dot(y, y, "cgo"), O.dot(u, y, "cgo"),
+                  O.dot(y, g1, "cgo"), O.dot(g1, g0, "cgo"), O.dot(u, g0, "cgo"), O.dot(u, u, "cgo")]
+        assert [float(v) for v in P[:9]] == expect
+        # literal β pass and ‖u + g‖
+        R, m = P[4], 2 * P[3] / P[4]
+        assert ws.beta_literal(R, m) == O.dot(y - m * u, g1 / R, "cgo")
+        assert ws.norm_u_plus_g() == 0.0
+        ws.close()
+    finally:
+        ctx.set_reduction_ctas(1184)
+        O.set_cgo_order(1184, 1)
+
+
+def test_fused_direction_equals_unfused(ctx):
+    """cgo_eval_trial_fused_dir ≡ cgo_update_dir + cgo_eval_trial, bit for bit."""
+    n = 50_000
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.1)
+    packs = []
+    for fuse in (False, True):
+        ws = obj.make_workspace(x0, fuse_direction=fuse)
+        ws.reset_direction()
+        ws.eval_trial(1e-3)
+        ws.accept()
+        ws.update_dir(0.37)
+        ws.hint_first_trial(2e-3)
+        gu, uu = ws.dot_g_u(), ws.dot_u_u()
+        ws.eval_trial(2e-3)
+        packs.append((gu, uu, ws.pack[:9].copy(), ws.download_vector("u"), ws.download_vector("df_xp")))
+        ws.close()
+    assert packs[0][0] == packs[1][0] and packs[0][1] == packs[1][1]
+    assert np.array_equal(packs[0][2], packs[1][2])
+    assert np.array_equal(packs[0][3], packs[1][3]) and np.array_equal(packs[0][4], packs[1][4])
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("linesearch", LINESEARCHES)
+def test_full_run_bit_exact_n1e4(ctx, flavour, linesearch):
+    """BASELINE.json configs[0] (n = 10,000) for every flavour × line search: the whole trace
+    (f, ‖g‖, step sizes, fdf evals, status, minimiser) is bit-identical to the oracle."""
+    n = 10_000
+    ocfg, cfg, ls = make_pair(flavour, linesearch, max_iters=120)
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.1)
+    ora = O.minimize(O.Objective.rosenbrock(n), x0, ocfg)
+    ret = cg.minimizeobjective(obj, x0, cfg, ls)
+    assert_same_run(ret, ora, what=f"{flavour}/{linesearch}")
+
+
+@pytest.mark.parametrize("flavour", ["HagerZhang", "YuanWangSheng"])
+def test_literal_beta_bit_exact(ctx, flavour):
+    """beta_form='literal' follows cg_flavours.jl:71-76 / :100-105 as written; bit-identical to
+    the oracle's literal restatement over the whole canonical config-1 run."""
+    n = 10_000
+    ocfg, cfg, ls = make_pair(flavour, beta_form="literal")
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.0)       # the standard start (−1.2, 1, …) of cfg 1
+    ora = O.minimize(O.Objective.rosenbrock(n), x0, ocfg)
+    ret = cg.minimizeobjective(obj, x0, cfg, ls, beta_form="literal")
+    assert ora.status == "success"
+    assert_same_run(ret, ora, what=flavour)
+
+
+def test_north_star_gates_vs_reference_shaped_oracle(ctx):
+    """The fused GPU path against the oracle in the reference's own shape (sequential sums,
+    literal β): north_star's tolerance gates hold on the window before the nonlinear-CG
+    trajectory's intrinsic chaos amplifies rounding differences."""
+    n = 10_000
+    ocfg, cfg, ls = make_pair("HagerZhang", sum_mode="seq", beta_form="literal")
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.1)
+    ora = O.minimize(O.Objective.rosenbrock(n), x0, ocfg)
+    ret = cg.minimizeobjective(obj, x0, cfg, ls)
+    k = 20
+    np.testing.assert_allclose(ret.trace.objective[:k], ora.trace_objective[:k], rtol=1e-10)
+    np.testing.assert_allclose(ret.trace.grad_norm[:k], ora.trace_grad_norm[:k], rtol=1e-10)
+    assert np.array_equal(ret.trace.step_size[:50], ora.trace_step_size[:50])
+    assert np.array_equal(ret.trace.objective_evals[:50], ora.trace_objective_evals[:50])
+    assert ret.status == ora.status == "success"
+    assert abs(ret.objective - ora.objective) <= 1e-8 * max(abs(ora.objective), 1.0)
+
+
+def test_run_to_run_reproducible(ctx):
+    n = 200_000
+    _, cfg, ls = make_pair(max_iters=30)
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.1)
+    a = cg.minimizeobjective(obj, x0, cfg, ls)
+    b = cg.minimizeobjective(obj, x0, cfg, ls, fuse_direction=False)
+    assert np.array_equal(a.trace.objective, b.trace.objective)
+    assert np.array_equal(a.minimizer, b.minimizer) and np.array_equal(a.gradient, b.gradient)
+
+
+def test_large_n_properties(ctx):
+    """n = 1e8 (BASELINE.json configs[1]) through size-independent properties: with the
+    unperturbed periodic start every pair is identical, so f = (n/2)·f_pair exactly representable
+    relations hold, the accepted steps equal those of the n = 1e4 oracle run only in decisions."""
+    n = 100_000_000
+    _, cfg, ls = make_pair(max_iters=8)
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.0)
+    ret = cg.minimizeobjective(obj, x0, cfg, ls)
+    # the problem is 2-periodic: the minimiser and gradient must stay exactly 2-periodic
+    x = ret.minimizer
+    assert np.all(x[0::2] == x[0]) and np.all(x[1::2] == x[1])
+    g = ret.gradient
+    assert np.all(g[0::2] == g[0]) and np.all(g[1::2] == g[1])
+    # per-pair objective equals the 1-pair oracle objective scaled by n/2 to 1e-12 (summation only)
+    xp = np.array([x[0], x[1]])
+    f1, _ = O.Objective.rosenbrock(2).fdf(xp)
+    assert abs(ret.objective - f1 * (n // 2)) <= 1e-12 * abs(ret.objective)
+    assert ret.iters_ran == 8 and np.all(np.diff(ret.trace.objective) < 0)
