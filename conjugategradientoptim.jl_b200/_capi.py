@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcgoptim.so")
 PACK_LEN = 16
 # pack indices (include/cgoptim.h)
-P_PHI, P_DPHI, P_GPGP, P_YY, P_UY, P_YGP, P_GPG, P_UG, P_UU = range(9)
+P_PHI, P_DPHI, P_GPGP, P_YY, P_UY, P_YGP, P_GPG, P_UG, P_UU, P_DIR_GU, P_DIR_UU, P_XPXP = range(12)
 D_GU, D_UU = 0, 1
 
 _lib = None

@@ -350,7 +350,10 @@ struct RosenObj : cgo_obj {
             op.xp = (double2 *)st->xp; op.gp = (double2 *)st->gp; op.a = a; op.beta = 0.0;
             CGO_TRY(launch_blas1(ctx, op, st->n, red));
         }
-        return cgo_finish_pack(ctx, 9, out);
+        CGO_TRY(cgo_finish_pack(ctx, 9, out));
+        out[CGO_P_DIR_GU] = out[CGO_P_UG];     // same kernel, same (V=2,U=4) site
+        out[CGO_P_DIR_UU] = out[CGO_P_UU];
+        return 0;
     }
     // fused minimum: R x,g,u ; W (u,) xp, g⁺
     double bytes_per_eval() const override { return 8.0 * 5.0 * (double)n_local; }
@@ -514,18 +517,19 @@ extern "C" int cgo_norm_sq_u_plus_g(cgo_state *st, double *outv) {
     return 0;
 }
 
-int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta, bool) {
-    // writes {g·u, u·u, xp·xp} to the reduction output (device pack slots 0..2)
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta) {
+    // writes {g·u, u·u, xp·xp} to pack slots CGO_P_DIR_GU, CGO_P_DIR_UU, CGO_P_XPXP
+    const RedArgs red = cgo_red_args(st->ctx, CGO_P_DIR_GU);
     if (fused) {
         AxpyDir<true> op;
         op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
         op.xp = (double2 *)st->xp; op.a = a; op.beta = beta;
-        return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx));
+        return launch_blas1(st->ctx, op, st->n, red);
     }
     AxpyDir<false> op;
     op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
     op.xp = (double2 *)st->xp; op.a = a; op.beta = 0.0;
-    return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx));
+    return launch_blas1(st->ctx, op, st->n, red);
 }
 
 // ------------------------------------------------------------------ L-BFGS

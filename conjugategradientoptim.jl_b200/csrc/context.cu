@@ -235,11 +235,11 @@ extern "C" int cgo_ctx_timing_read(cgo_ctx *c, double *ms, int64_t *counts, int 
 }
 
 // ------------------------------------------------------------------ scalar pack finish
-RedArgs cgo_red_args(cgo_ctx *c) {
+RedArgs cgo_red_args(cgo_ctx *c, int slot) {
     RedArgs r;
     r.partial = c->d_partial;
     r.ticket = c->d_ticket;
-    r.out = (c->nranks > 1) ? c->d_pack : c->d_pack_map;
+    r.out = ((c->nranks > 1) ? c->d_pack : c->d_pack_map) + slot;
     r.G = c->G;
     return r;
 }

@@ -1,0 +1,681 @@
+// csr.cu — CSR objectives: sparse least squares ½‖Ax − b‖² and logistic regression.
+//
+// These are device-resident replacements of the user callback `fdf!(g, x) -> f` that the
+// reference calls at src/engine/optim.jl:25 and src/cg_utils.jl:18 (the reference ships no
+// large objective; the definitions are restated in oracle/cgo_oracle.c
+// sparse_ls_fdf / logreg_fdf).  One trial  evalϕdϕ! (src/cg_utils.jl:3-22)  is three kernels:
+//   K_a  xp = x + a u  [after u = −g + βu, cg_flavours.jl:10-12]           BLAS-1, blas1.cu
+//   K_b  r  = A xp − b,  Σ r²                (logreg: margins, loss, c)     k_csr_rows
+//   K_c  g⁺ = Aᵀ r  + every dot of getβ / norm(df_xp) / dϕ                  k_csr_rows on Aᵀ
+// Aᵀ is an explicit CSR whose rows are sorted by source entry, so the gradient is a gather
+// (no atomics on data) and reproduces the sequential scatter order of the oracle bit for bit.
+//
+// k_csr_rows is a "CSR-stream" kernel: a CTA owns 256 consecutive rows; their nonzeros are one
+// contiguous range of val/col that the CTA streams with fully coalesced loads (10 independent
+// 12-byte loads per lane in flight), multiplies with the gathered vector entry and parks in
+// shared memory; lane t then adds up row t's products in storage order.  Rows of any length
+// work (the range is walked in chunks of 2560 entries).
+#include <cub/device/device_scan.cuh>
+
+#include "internal.cuh"
+#include "reduce.cuh"
+
+constexpr int CSR_UN = 10;                  // entries per lane per chunk
+constexpr int CSR_CH = CGO_B * CSR_UN;      // entries per chunk (20 KB of products)
+constexpr int CSR_OCC = 4;
+
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f64(double *p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Canonical reduction site of these kernels: V = 1, U = 1 (item = row; include/cgoptim.h).
+template <class Epi>
+__global__ void __launch_bounds__(CGO_B, CSR_OCC)
+k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
+    constexpr int K = Epi::K;
+    __shared__ double prod[CSR_CH];
+    __shared__ double sm[K * CGO_NW];
+    __shared__ int64_t s_range[2];
+    const int tid = threadIdx.x;
+    const int64_t nrows = A.nrows;
+    const int64_t ntiles = (nrows + CGO_B - 1) / CGO_B;
+    const int nact = (int)(ntiles < (int64_t)red.G ? ntiles : (int64_t)red.G);
+    for (int v = blockIdx.x; v < nact; v += gridDim.x) {
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int64_t tile = v; tile < ntiles; tile += red.G) {
+            const int64_t row = tile * CGO_B + tid;
+            const bool valid = row < nrows;
+            int64_t rs = 0, re = 0;
+            if (valid) { rs = __ldg(A.rowptr + row); re = __ldg(A.rowptr + row + 1); }
+            if (tid == 0) s_range[0] = rs;
+            if (valid && (tid == CGO_B - 1 || row == nrows - 1)) s_range[1] = re;
+            __syncthreads();
+            const int64_t p0 = s_range[0], p1 = s_range[1];
+            double sum = 0.0;
+            for (int64_t c0 = p0; c0 < p1; c0 += CSR_CH) {
+                int32_t cj[CSR_UN];
+                double vj[CSR_UN];
+#pragma unroll
+                for (int j = 0; j < CSR_UN; ++j) {
+                    const int64_t p = c0 + tid + j * CGO_B;
+                    if (p < p1) { cj[j] = ld_stream_s32(A.col + p); vj[j] = ld_stream_f64(A.val + p); }
+                }
+#pragma unroll
+                for (int j = 0; j < CSR_UN; ++j) {
+                    const int64_t p = c0 + tid + j * CGO_B;
+                    if (p < p1) prod[tid + j * CGO_B] = vj[j] * __ldg(xg + cj[j]);
+                }
+                __syncthreads();
+                int64_t lo = rs > c0 ? rs : c0;
+                int64_t hi = re < c0 + CSR_CH ? re : c0 + CSR_CH;
+                for (int64_t p = lo; p < hi; ++p) sum = sum + prod[p - c0];
+                __syncthreads();
+            }
+            if (valid) epi.row(row, sum, acc);
+            __syncthreads();      // s_range is rewritten by the next tile
+        }
+        cgo_cta_combine<K>(acc, sm);
+        cgo_publish<K>(red, v, acc);
+    }
+    cgo_grid_finish<K>(red, nact, sm);
+}
+
+template <class Epi>
+static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
+    const int64_t ntiles = (A.nrows + CGO_B - 1) / CGO_B;
+    int64_t nact = ntiles < red.G ? ntiles : red.G;
+    int64_t phys = (int64_t)c->sms * CSR_OCC;
+    int grid = (int)(nact < phys ? nact : phys);
+    if (grid < 1) grid = 1;
+    cgo_timer_begin(c, tclass);
+    k_csr_rows<Epi><<<grid, CGO_B, 0, c->stream>>>(A, xg, epi, red);
+    cgo_timer_end(c);
+    c->launches++;
+    CGO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ row epilogues
+struct EpiStore {                       // y = A x
+    static constexpr int K = 1;
+    double *y;
+    __device__ __forceinline__ void row(int64_t i, double sum, double (&)[K]) const { y[i] = sum; }
+};
+struct EpiResidual {                    // r = A xp − b ; Σ r²
+    static constexpr int K = 1;
+    const double *b;
+    double *r;
+    __device__ __forceinline__ void row(int64_t i, double sum, double (&acc)[K]) const {
+        const double rr = sum - ld_stream_f64(b + i);
+        r[i] = rr;                      // re-read (gathered) by K_c: keep it cacheable
+        acc[0] = acc[0] + rr * rr;
+    }
+};
+// g⁺ = Aᵀ r [· 1/N + λ w], fused with norm(df_xp)² (optim.jl:107), dϕ = g⁺·u (cg_utils.jl:20) and
+// the getβ dots (cg_flavours.jl:63-76, 96-105, 140-145, 164-167); fills pack slots 1..8.
+template <bool LOGREG>
+struct EpiGrad {
+    static constexpr int K = 8;
+    double *gp;
+    const double *g, *u, *w;
+    double invN, lambda;
+    __device__ __forceinline__ void row(int64_t j, double sum, double (&acc)[K]) const {
+        double gn = sum;
+        if (LOGREG) gn = sum * invN + lambda * ld_stream_f64(w + j);
+        st_stream_f64(gp + j, gn);
+        const double uu = ld_stream_f64(u + j), gg = ld_stream_f64(g + j);
+        const double y = gn - gg;
+        acc[CGO_P_DPHI - 1] = acc[CGO_P_DPHI - 1] + gn * uu;
+        acc[CGO_P_GPGP - 1] = acc[CGO_P_GPGP - 1] + gn * gn;
+        acc[CGO_P_YY - 1] = acc[CGO_P_YY - 1] + y * y;
+        acc[CGO_P_UY - 1] = acc[CGO_P_UY - 1] + uu * y;
+        acc[CGO_P_YGP - 1] = acc[CGO_P_YGP - 1] + y * gn;
+        acc[CGO_P_GPG - 1] = acc[CGO_P_GPG - 1] + gn * gg;
+        acc[CGO_P_UG - 1] = acc[CGO_P_UG - 1] + uu * gg;
+        acc[CGO_P_UU - 1] = acc[CGO_P_UU - 1] + uu * uu;
+    }
+};
+// logistic loss of sample i with margin z = a_i·w (oracle logreg_fdf):
+//   t = −y z; e = exp(−|t|); ℓ = max(t,0) + log1p(e); σ = t ≥ 0 ? 1/(1+e) : e/(1+e); c = −y σ
+struct EpiLogit {
+    static constexpr int K = 1;
+    const double *label;
+    double *c;
+    __device__ __forceinline__ void row(int64_t i, double z, double (&acc)[K]) const {
+        const double y = ld_stream_f64(label + i);
+        const double t = -y * z;
+        const double e = exp(-fabs(t));
+        const double l = (t > 0.0 ? t : 0.0) + log1p(e);
+        const double sg = t >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+        c[i] = -y * sg;
+        acc[0] = acc[0] + l;
+    }
+};
+
+// ------------------------------------------------------------------ counter-based hash
+// (generator spec: oracle/cgo_oracle.c hash3 / u01; restated, identical arithmetic)
+__host__ __device__ __forceinline__ uint64_t g_mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+__host__ __device__ __forceinline__ uint64_t g_hash3(uint64_t seed, uint64_t i, uint64_t k) {
+    uint64_t h = g_mix64(seed + 0x9E3779B97F4A7C15ULL);
+    h = g_mix64(h ^ (i + 0x9E3779B97F4A7C15ULL));
+    h = g_mix64(h ^ (k + 0x632BE59BD9B4E019ULL));
+    return h;
+}
+__host__ __device__ __forceinline__ double g_u01(uint64_t seed, uint64_t i, uint64_t k) {
+    return (double)(g_hash3(seed, i, k) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// banded-random least-squares generator (spec text: oracle/cgo_oracle.c orc_obj_sparse_ls_synth)
+struct LsSpec {
+    int64_t n;          // global dimension
+    int32_t K;          // entries per row
+    int32_t coh;        // log2 of the number of consecutive rows sharing their offsets
+    int64_t W, w;       // half band width, stratum width 2W/(K−1)
+    uint64_t seed;
+    // signed column offset and value of entry k of global row i
+    __host__ __device__ __forceinline__ void entry(int64_t i, int k, int64_t &d, double &v) const {
+        if (k == 0) { d = 0; v = 4.0 + g_u01(seed, (uint64_t)i, 0); return; }
+        const int64_t lo = -W + (int64_t)(k - 1) * w;
+        d = lo + (int64_t)(g_hash3(seed ^ 0xA5A5A5A5A5A5A5A5ULL, (uint64_t)(i >> coh), (uint64_t)k) % (uint64_t)w);
+        if (d == 0) d = (lo + w > 1) ? 1 : -1;
+        v = 0.3 * (2.0 * g_u01(seed, (uint64_t)i, (uint64_t)k) - 1.0);
+    }
+    __host__ __device__ __forceinline__ int64_t wrap(int64_t c) const {
+        if (c < 0) c += n;
+        if (c >= n) c -= n;
+        return c;
+    }
+};
+// logistic-regression generator (spec text: oracle/cgo_oracle.c orc_obj_logreg_synth)
+struct LrSpec {
+    int64_t N, d;
+    int32_t K;
+    int64_t w;          // stratum width d / K
+    uint64_t seed;
+    __host__ __device__ __forceinline__ void entry(int64_t i, int k, int64_t &c, double &v) const {
+        c = (int64_t)k * w + (int64_t)(g_hash3(seed, (uint64_t)i, (uint64_t)k) % (uint64_t)w);
+        v = 2.0 * g_u01(seed + 7, (uint64_t)i, (uint64_t)k) - 1.0;
+    }
+};
+
+static inline int grid_for(int64_t items, int sms) {
+    int64_t b = (items + 255) / 256;
+    int64_t cap = (int64_t)sms * 32;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+#define GRID_STRIDE(idx, total) \
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (total); idx += (int64_t)gridDim.x * blockDim.x)
+
+// rows [lo, lo + nloc) of A.  unwrapped: column index relative to lo, in [−W, nloc + W) (halo
+// layout, multi-rank); else the wrapped global column (single rank).
+__global__ void k_ls_fill_A(LsSpec s, int64_t lo, int64_t nloc, bool unwrapped, CsrMat A) {
+    const int64_t total = nloc * s.K;
+    GRID_STRIDE(p, total) {
+        const int64_t il = p / s.K;
+        const int k = (int)(p - il * s.K);
+        int64_t d; double v;
+        s.entry(lo + il, k, d, v);
+        A.col[p] = (int32_t)(unwrapped ? il + d : s.wrap(lo + il + d));
+        A.val[p] = v;
+        if (k == 0) A.rowptr[il] = p;
+        if (p == total - 1) A.rowptr[nloc] = total;
+    }
+}
+// x_true over [lo − halo, lo + nloc + halo), wrapped
+__global__ void k_ls_xtrue(LsSpec s, int64_t lo, int64_t nloc, int64_t halo, double *xt /* local origin */) {
+    GRID_STRIDE(e, nloc + 2 * halo) {
+        int64_t i = s.wrap(lo - halo + e);
+        xt[e - halo] = 2.0 * g_u01(s.seed + 1, (uint64_t)i, 0) - 1.0;
+    }
+}
+__global__ void k_lr_fill_A(LrSpec s, CsrMat A, double *label) {
+    GRID_STRIDE(i, s.N) {
+        const int64_t p = i * s.K;
+        A.rowptr[i] = p;
+        double acc = 0.0;
+        for (int k = 0; k < s.K; ++k) {
+            int64_t c; double v;
+            s.entry(i, k, c, v);
+            A.col[p + k] = (int32_t)c;
+            A.val[p + k] = v;
+            const double wt = 2.0 * g_u01(s.seed + 2, (uint64_t)c, 0) - 1.0;
+            acc += v * wt;
+        }
+        const double noise = 2.0 * g_u01(s.seed + 3, (uint64_t)i, 0) - 1.0;
+        label[i] = (acc + 0.1 * noise >= 0.0) ? 1.0 : -1.0;
+        if (i == s.N - 1) A.rowptr[s.N] = s.N * s.K;
+    }
+}
+
+// ------------------------------------------------------------------ explicit transpose (setup)
+// Entry sources enumerate (target row of Aᵀ, sort key) pairs; keys order the entries of one Aᵀ
+// row exactly like the oracle's stable counting sort (ascending source entry).
+struct CsrSrc {                 // a materialised CSR on this device
+    const int32_t *col;
+    int64_t total;
+    __device__ __forceinline__ bool get(int64_t e, int64_t &trow, int64_t &key) const {
+        trow = col[e]; key = e;
+        return true;
+    }
+};
+struct LsExtSrc {               // generator rows [lo − W, hi + W): entries landing in columns [lo, hi)
+    LsSpec s;
+    int64_t lo, hi, total;
+    __device__ __forceinline__ bool get(int64_t e, int64_t &trow, int64_t &key) const {
+        const int64_t ie = e / s.K;
+        const int k = (int)(e - ie * s.K);
+        const int64_t i = s.wrap(lo - s.W + ie);
+        int64_t d; double v;
+        s.entry(i, k, d, v);
+        const int64_t c = s.wrap(i + d);
+        if (c < lo || c >= hi) return false;
+        trow = c - lo; key = i * s.K + k;
+        return true;
+    }
+};
+template <class Src>
+__global__ void k_tr_count(Src src, unsigned long long *counts) {
+    GRID_STRIDE(e, src.total) {
+        int64_t trow, key;
+        if (src.get(e, trow, key)) atomicAdd(counts + trow, 1ULL);
+    }
+}
+template <class Src>
+__global__ void k_tr_fill(Src src, unsigned long long *cursor, int64_t *perm) {
+    GRID_STRIDE(e, src.total) {
+        int64_t trow, key;
+        if (src.get(e, trow, key)) perm[atomicAdd(cursor + trow, 1ULL)] = key;
+    }
+}
+// each Aᵀ row's keys ascending (insertion sort for short rows, heapsort beyond)
+__global__ void k_tr_sort(const int64_t *rowptrT, int64_t nT, int64_t *perm) {
+    GRID_STRIDE(j, nT) {
+        int64_t *a = perm + rowptrT[j];
+        const int64_t L = rowptrT[j + 1] - rowptrT[j];
+        if (L <= 48) {
+            for (int64_t i = 1; i < L; ++i) {
+                const int64_t key = a[i];
+                int64_t q = i - 1;
+                while (q >= 0 && a[q] > key) { a[q + 1] = a[q]; --q; }
+                a[q + 1] = key;
+            }
+        } else {
+            for (int64_t start = L / 2 - 1; start >= 0; --start) {       // heapify
+                int64_t root = start;
+                for (;;) {
+                    int64_t ch = 2 * root + 1;
+                    if (ch >= L) break;
+                    if (ch + 1 < L && a[ch] < a[ch + 1]) ++ch;
+                    if (a[root] >= a[ch]) break;
+                    int64_t t = a[root]; a[root] = a[ch]; a[ch] = t;
+                    root = ch;
+                }
+            }
+            for (int64_t end = L - 1; end > 0; --end) {
+                int64_t t = a[0]; a[0] = a[end]; a[end] = t;
+                int64_t root = 0;
+                for (;;) {
+                    int64_t ch = 2 * root + 1;
+                    if (ch >= end) break;
+                    if (ch + 1 < end && a[ch] < a[ch + 1]) ++ch;
+                    if (a[root] >= a[ch]) break;
+                    int64_t t2 = a[root]; a[root] = a[ch]; a[ch] = t2;
+                    root = ch;
+                }
+            }
+        }
+    }
+}
+struct CsrFin {                 // key = entry index of a materialised CSR
+    const int64_t *rowptr;
+    int64_t nrows;
+    const double *val;
+    __device__ __forceinline__ void get(int64_t key, int32_t &srow, double &v) const {
+        int64_t lo = 0, hi = nrows;              // last row with rowptr[row] <= key
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= key) lo = mid; else hi = mid;
+        }
+        srow = (int32_t)lo; v = val[key];
+    }
+};
+struct FixedKFin {              // materialised CSR with exactly K entries per row
+    int32_t K;
+    const double *val;
+    __device__ __forceinline__ void get(int64_t key, int32_t &srow, double &v) const {
+        srow = (int32_t)(key / K); v = val[key];
+    }
+};
+struct LsExtFin {               // key = global entry index of the generator
+    LsSpec s;
+    int64_t lo;
+    __device__ __forceinline__ void get(int64_t key, int32_t &srow, double &v) const {
+        const int64_t i = key / s.K;
+        const int k = (int)(key - i * s.K);
+        int64_t d;
+        s.entry(i, k, d, v);
+        int64_t rel = i - lo;                    // unwrapped position relative to this shard
+        if (rel < -s.W) rel += s.n;
+        if (rel >= s.n - s.W) rel -= s.n;
+        srow = (int32_t)rel;
+    }
+};
+template <class Fin>
+__global__ void k_tr_finalize(Fin fin, int64_t nnzT, const int64_t *perm, CsrMat AT) {
+    GRID_STRIDE(q, nnzT) {
+        int32_t srow; double v;
+        fin.get(perm[q], srow, v);
+        AT.col[q] = srow;
+        AT.val[q] = v;
+    }
+}
+
+static void csr_free(CsrMat &M) {
+    cudaFree(M.rowptr); cudaFree(M.col); cudaFree(M.val);
+    M = CsrMat();
+}
+static int csr_alloc(CsrMat &M, int64_t nrows, int64_t nnz) {
+    M.nrows = nrows; M.nnz = nnz;
+    CGO_CUDA(cudaMalloc(&M.rowptr, sizeof(int64_t) * (size_t)(nrows + 1)));
+    CGO_CUDA(cudaMalloc(&M.col, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    CGO_CUDA(cudaMalloc(&M.val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    return 0;
+}
+
+template <class Src, class Fin>
+static int build_transpose(cgo_ctx *c, const Src &src, const Fin &fin, int64_t nT, CsrMat &AT) {
+    cudaStream_t s = c->stream;
+    unsigned long long *counts = nullptr, *cursor = nullptr;
+    int64_t *perm = nullptr;
+    void *tmp = nullptr;
+    int rc = 0;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&counts, sizeof(unsigned long long) * (size_t)(nT + 1)));
+        CGO_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)(nT + 1), s));
+        if (src.total > 0) k_tr_count<<<grid_for(src.total, c->sms), 256, 0, s>>>(src, counts);
+        CGO_CUDA(cudaGetLastError());
+        AT.nrows = nT;
+        CGO_CUDA(cudaMalloc(&AT.rowptr, sizeof(int64_t) * (size_t)(nT + 1)));
+        size_t tmp_bytes = 0;
+        CGO_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int64_t *)counts, AT.rowptr, nT + 1, s));
+        CGO_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+        CGO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int64_t *)counts, AT.rowptr, nT + 1, s));
+        int64_t nnzT = 0;
+        CGO_CUDA(cudaMemcpyAsync(&nnzT, AT.rowptr + nT, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CGO_CUDA(cudaStreamSynchronize(s));
+        AT.nnz = nnzT;
+        cudaFree(counts); counts = nullptr;
+        cudaFree(tmp); tmp = nullptr;
+        CGO_CUDA(cudaMalloc(&cursor, sizeof(unsigned long long) * (size_t)(nT + 1)));
+        CGO_CUDA(cudaMemcpyAsync(cursor, AT.rowptr, sizeof(int64_t) * (size_t)(nT + 1), cudaMemcpyDeviceToDevice, s));
+        CGO_CUDA(cudaMalloc(&perm, sizeof(int64_t) * (size_t)(nnzT > 0 ? nnzT : 1)));
+        if (src.total > 0) k_tr_fill<<<grid_for(src.total, c->sms), 256, 0, s>>>(src, cursor, perm);
+        CGO_CUDA(cudaGetLastError());
+        if (nT > 0) k_tr_sort<<<grid_for(nT, c->sms), 256, 0, s>>>(AT.rowptr, nT, perm);
+        CGO_CUDA(cudaGetLastError());
+        CGO_CUDA(cudaMalloc(&AT.col, sizeof(int32_t) * (size_t)(nnzT > 0 ? nnzT : 1)));
+        CGO_CUDA(cudaMalloc(&AT.val, sizeof(double) * (size_t)(nnzT > 0 ? nnzT : 1)));
+        if (nnzT > 0) k_tr_finalize<<<grid_for(nnzT, c->sms), 256, 0, s>>>(fin, nnzT, perm, AT);
+        CGO_CUDA(cudaGetLastError());
+        CGO_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    };
+    rc = body();
+    cudaFree(counts); cudaFree(cursor); cudaFree(perm); cudaFree(tmp);
+    return rc;
+}
+
+// ------------------------------------------------------------------ the objective
+struct CsrObj : cgo_obj {
+    bool logreg = false;
+    CsrMat A, AT;
+    int64_t nrows = 0;                 // local rows of A (residuals / samples)
+    double *b = nullptr;               // rhs (LS) or labels (logreg), nrows
+    double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
+    double lambda = 0.0;
+    int64_t nsamples = 0;
+    ~CsrObj() override {
+        if (ctx) cudaSetDevice(ctx->device);
+        csr_free(A); csr_free(AT);
+        cudaFree(b); cudaFree(r_base);
+    }
+    int alloc_r() {
+        CGO_CUDA(cudaMalloc(&r_base, sizeof(double) * (size_t)(nrows + 2 * halo + 4)));
+        CGO_CUDA(cudaMemsetAsync(r_base, 0, sizeof(double) * (size_t)(nrows + 2 * halo + 4), ctx->stream));
+        r = r_base + halo;
+        return 0;
+    }
+    // fill v[−halo, 0) and v[nloc, nloc + halo) from the ring neighbours
+    int exchange(double *v, int64_t nloc) {
+        if (halo == 0) return 0;
+        return cgo_sendrecv_ring(ctx, v, v + nloc, v + nloc - halo, v - halo, halo);
+    }
+    int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                               // K_a
+        CGO_TRY(exchange(st->xp, st->n));
+        if (logreg) {
+            EpiLogit e1{b, r};
+            CGO_TRY(launch_csr(ctx, A, st->xp, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));   // K_b
+            EpiGrad<true> e2{st->gp, st->g, st->u, st->xp, 1.0 / (double)nsamples, lambda};
+            CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT));      // K_c
+            CGO_TRY(cgo_finish_pack(ctx, 12, out));
+            out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
+        } else {
+            EpiResidual e1{b, r};
+            CGO_TRY(launch_csr(ctx, A, st->xp, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));   // K_b
+            CGO_TRY(exchange(r, nrows));
+            EpiGrad<false> e2{st->gp, st->g, st->u, nullptr, 0.0, 0.0};
+            CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT));      // K_c
+            CGO_TRY(cgo_finish_pack(ctx, 12, out));
+            out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
+        }
+        return 0;
+    }
+    // A and Aᵀ streamed once (8 B value + 4 B index per entry + row pointers)
+    // plus the vector passes R x,u W xp | gather xp, R b, W r | gather r, W g⁺, R u (,g)
+    double bytes_per_eval() const override {
+        return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
+               8.0 * (3.0 * (double)nrows + 6.0 * (double)n_local);
+    }
+    int default_x0(uint64_t, double, double *x0) override {
+        for (int64_t i = 0; i < n_local; ++i) x0[i] = 0.0;
+        return 0;
+    }
+};
+
+static int check_i32(int64_t v, const char *what) {
+    CGO_CHECK(v < 2147483647LL, "%s = %lld does not fit the int32 column index", what, (long long)v);
+    return 0;
+}
+
+extern "C" int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n, int32_t K, int64_t W,
+                                                  uint64_t seed, int32_t coh_log2, cgo_obj **out) {
+    CGO_CHECK(ctx && out, "NULL argument");
+    const int64_t S = K - 1;
+    CGO_CHECK(K >= 1 && n >= 2 && n % 2 == 0, "sparse_ls: need nnz_per_row >= 1 and an even n >= 2");
+    CGO_CHECK(S == 0 || (W >= S && n > 2 * W), "sparse_ls: need W >= nnz_per_row-1 and n > 2W (n=%lld, W=%lld)", (long long)n, (long long)W);
+    CGO_CHECK(coh_log2 >= 0 && coh_log2 < 31, "sparse_ls: coh_log2 out of range");
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    CsrObj *o = new CsrObj();
+    o->ctx = ctx; o->n_global = n;
+    int64_t lo, hi;
+    CGO_TRY(cgo_shard_range(n, ctx->nranks, ctx->rank, 2, &lo, &hi));
+    o->offset = lo; o->n_local = hi - lo; o->nrows = hi - lo;
+    const bool multi = ctx->nranks > 1;
+    o->halo = multi ? W : 0;
+    if (multi) {
+        if (o->n_local < W || o->n_local + 2 * W > n) {
+            cgo_set_error("sparse_ls: shard of %lld rows needs W <= rows and rows + 2W <= n (W=%lld, n=%lld)",
+                          (long long)o->n_local, (long long)W, (long long)n);
+            delete o;
+            return 2;
+        }
+        CGO_CHECK(W % 2 == 0, "sparse_ls: W must be even with more than one rank");
+    }
+    LsSpec sp;
+    sp.n = n; sp.K = K; sp.coh = coh_log2; sp.W = W; sp.w = S > 0 ? (2 * W) / S : 0; sp.seed = seed;
+    const int64_t nloc = o->n_local, nnz = nloc * K;
+    double *xt_base = nullptr;
+    auto body = [&]() -> int {
+        CGO_TRY(check_i32(nloc + 2 * o->halo, "local dimension + halo"));
+        CGO_TRY(csr_alloc(o->A, nloc, nnz));
+        k_ls_fill_A<<<grid_for(nnz, ctx->sms), 256, 0, ctx->stream>>>(sp, lo, nloc, multi, o->A);
+        CGO_CUDA(cudaGetLastError());
+        // b = A x_true
+        CGO_CUDA(cudaMalloc(&xt_base, sizeof(double) * (size_t)(nloc + 2 * o->halo)));
+        k_ls_xtrue<<<grid_for(nloc + 2 * o->halo, ctx->sms), 256, 0, ctx->stream>>>(sp, lo, nloc, o->halo, xt_base + o->halo);
+        CGO_CUDA(cudaGetLastError());
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)nloc));
+        EpiStore es{o->b};
+        CGO_TRY(launch_csr(ctx, o->A, xt_base + o->halo, es, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_OTHER));
+        CGO_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(xt_base); xt_base = nullptr;
+        CGO_TRY(o->alloc_r());
+        if (multi) {
+            LsExtSrc src{sp, lo, hi, (nloc + 2 * W) * K};
+            LsExtFin fin{sp, lo};
+            CGO_TRY(build_transpose(ctx, src, fin, nloc, o->AT));
+        } else {
+            CsrSrc src{o->A.col, nnz};
+            FixedKFin fin{K, o->A.val};
+            CGO_TRY(build_transpose(ctx, src, fin, nloc, o->AT));
+        }
+        return 0;
+    };
+    int rc = body();
+    cudaFree(xt_base);
+    if (rc) { delete o; return rc; }
+    *out = o;
+    return 0;
+}
+
+extern "C" int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t ncols, const int64_t *rowptr,
+                                            const int32_t *col, const double *val, const double *b,
+                                            cgo_obj **out) {
+    CGO_CHECK(ctx && rowptr && b && out, "NULL argument");
+    CGO_CHECK(ctx->nranks == 1, "cgo_obj_sparse_ls_create_csr is single-GPU");
+    CGO_CHECK(nrows >= 1 && ncols >= 1, "empty matrix");
+    const int64_t nnz = rowptr[nrows];
+    CGO_CHECK(nnz == 0 || (col && val), "NULL col/val");
+    for (int64_t i = 0; i < nrows; ++i) CGO_CHECK(rowptr[i] <= rowptr[i + 1], "rowptr not monotone at row %lld", (long long)i);
+    for (int64_t p = 0; p < nnz; ++p) CGO_CHECK(col[p] >= 0 && col[p] < ncols, "column index out of range at entry %lld", (long long)p);
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    CsrObj *o = new CsrObj();
+    o->ctx = ctx; o->n_global = ncols; o->n_local = ncols; o->offset = 0; o->nrows = nrows; o->halo = 0;
+    auto body = [&]() -> int {
+        CGO_TRY(check_i32(nrows > ncols ? nrows : ncols, "matrix dimension"));
+        CGO_TRY(csr_alloc(o->A, nrows, nnz));
+        cudaStream_t s = ctx->stream;
+        CGO_CUDA(cudaMemcpyAsync(o->A.rowptr, rowptr, sizeof(int64_t) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, s));
+        if (nnz) {
+            CGO_CUDA(cudaMemcpyAsync(o->A.col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+            CGO_CUDA(cudaMemcpyAsync(o->A.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+        }
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)nrows));
+        CGO_CUDA(cudaMemcpyAsync(o->b, b, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, s));
+        CGO_TRY(o->alloc_r());
+        CsrSrc src{o->A.col, nnz};
+        CsrFin fin{o->A.rowptr, nrows, o->A.val};
+        CGO_TRY(build_transpose(ctx, src, fin, ncols, o->AT));
+        return 0;
+    };
+    int rc = body();
+    if (rc) { delete o; return rc; }
+    *out = o;
+    return 0;
+}
+
+extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t d, int32_t K, uint64_t seed,
+                                               double lambda, cgo_obj **out) {
+    CGO_CHECK(ctx && out, "NULL argument");
+    CGO_CHECK(ctx->nranks == 1, "cgo_obj_logreg_create_synthetic is single-GPU in this version");
+    CGO_CHECK(K >= 1 && N >= 1 && d >= K, "logreg: need nnz_per_row >= 1, nsamples >= 1, nfeat >= nnz_per_row");
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    CsrObj *o = new CsrObj();
+    o->ctx = ctx; o->logreg = true; o->lambda = lambda; o->nsamples = N;
+    o->n_global = d; o->n_local = d; o->offset = 0; o->nrows = N; o->halo = 0;
+    LrSpec sp;
+    sp.N = N; sp.d = d; sp.K = K; sp.w = d / K; sp.seed = seed;
+    auto body = [&]() -> int {
+        CGO_TRY(check_i32(N > d ? N : d, "matrix dimension"));
+        CGO_TRY(csr_alloc(o->A, N, N * K));
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)N));
+        k_lr_fill_A<<<grid_for(N, ctx->sms), 256, 0, ctx->stream>>>(sp, o->A, o->b);
+        CGO_CUDA(cudaGetLastError());
+        CGO_TRY(o->alloc_r());
+        CsrSrc src{o->A.col, N * K};
+        FixedKFin fin{K, o->A.val};
+        CGO_TRY(build_transpose(ctx, src, fin, d, o->AT));
+        return 0;
+    };
+    int rc = body();
+    if (rc) { delete o; return rc; }
+    *out = o;
+    return 0;
+}
+
+// ------------------------------------------------------------------ test hooks
+static CsrObj *as_csr(cgo_obj *o) { return dynamic_cast<CsrObj *>(o); }
+
+extern "C" int cgo_obj_csr_nnz(cgo_obj *obj, int transposed, int64_t *nrows, int64_t *nnz) {
+    CsrObj *o = as_csr(obj);
+    CGO_CHECK(o != nullptr, "not a CSR objective");
+    const CsrMat &M = transposed ? o->AT : o->A;
+    if (nrows) *nrows = M.nrows;
+    if (nnz) *nnz = M.nnz;
+    return 0;
+}
+extern "C" int cgo_obj_csr_download(cgo_obj *obj, int transposed, int64_t *rowptr, int32_t *col, double *val, double *b) {
+    CsrObj *o = as_csr(obj);
+    CGO_CHECK(o != nullptr, "not a CSR objective");
+    const CsrMat &M = transposed ? o->AT : o->A;
+    cudaStream_t s = o->ctx->stream;
+    CGO_CUDA(cudaSetDevice(o->ctx->device));
+    if (rowptr) CGO_CUDA(cudaMemcpyAsync(rowptr, M.rowptr, sizeof(int64_t) * (size_t)(M.nrows + 1), cudaMemcpyDeviceToHost, s));
+    if (col && M.nnz) CGO_CUDA(cudaMemcpyAsync(col, M.col, sizeof(int32_t) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
+    if (val && M.nnz) CGO_CUDA(cudaMemcpyAsync(val, M.val, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
+    if (b) CGO_CUDA(cudaMemcpyAsync(b, o->b, sizeof(double) * (size_t)o->nrows, cudaMemcpyDeviceToHost, s));
+    CGO_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+// y = A x (transposed: Aᵀ x) through the production kernel; single GPU (no halo)
+extern "C" int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, double *y_host) {
+    CsrObj *o = as_csr(obj);
+    CGO_CHECK(o && x_host && y_host, "not a CSR objective / NULL argument");
+    CGO_CHECK(o->halo == 0, "cgo_obj_spmv is a single-GPU test hook");
+    cgo_ctx *c = o->ctx;
+    CGO_CUDA(cudaSetDevice(c->device));
+    const CsrMat &M = transposed ? o->AT : o->A;
+    const int64_t nin = transposed ? o->A.nrows : o->AT.nrows, nout = M.nrows;
+    double *dx = nullptr, *dy = nullptr;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&dx, sizeof(double) * (size_t)nin));
+        CGO_CUDA(cudaMalloc(&dy, sizeof(double) * (size_t)nout));
+        CGO_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * (size_t)nin, cudaMemcpyHostToDevice, c->stream));
+        EpiStore es{dy};
+        CGO_TRY(launch_csr(c, M, dx, es, cgo_red_args(c, CGO_PACK_LEN - 1), transposed ? CGO_T_SPMVT : CGO_T_SPMV));
+        CGO_CUDA(cudaMemcpyAsync(y_host, dy, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
+        CGO_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    int rc = body();
+    cudaFree(dx); cudaFree(dy);
+    return rc;
+}

@@ -83,7 +83,8 @@ constexpr int CGO_LBFGS_MAX_M = 64;
 
 // launch the pack finalisation for the current kernel sequence: after the producing kernel
 // wrote K sums to ctx->red_out(), make them visible on the host in out[0..K).
-RedArgs cgo_red_args(cgo_ctx *ctx);
+// `slot`: first pack slot the kernel's K sums land in (kernels of one trial fill disjoint slots)
+RedArgs cgo_red_args(cgo_ctx *ctx, int slot = 0);
 void cgo_timer_begin(cgo_ctx *ctx, int cls);   // records an event on the ctx stream (if enabled)
 void cgo_timer_end(cgo_ctx *ctx);
 void cgo_timer_collect(cgo_ctx *ctx);          // after a stream sync: fold pending timers
@@ -123,4 +124,14 @@ struct cgo_state {
 };
 
 // BLAS-1 kernels shared by objectives (blas1.cu)
-int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, bool want_ww);
+// xp = x + a u (optionally after u = −g + βu); {g·u, u·u, xp·xp} land in pack slots
+// CGO_P_DIR_GU, CGO_P_DIR_UU, CGO_P_XPXP
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta);
+
+// ------------------------------------------------------------------ CSR (csr.cu)
+struct CsrMat {
+    int64_t nrows = 0, nnz = 0;
+    int64_t *rowptr = nullptr;   // nrows + 1
+    int32_t *col = nullptr;      // index into the gathered vector (may be negative: left halo)
+    double *val = nullptr;
+};

@@ -16,7 +16,7 @@ from typing import Optional
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (D_GU, D_UU, P_DPHI, P_GPG, P_GPGP, P_PHI, P_UG, P_UU, P_UY, P_YGP, P_YY,
+from ._capi import (D_GU, D_UU, P_DIR_GU, P_DIR_UU, P_DPHI, P_GPG, P_GPGP, P_PHI, P_UG, P_UU, P_UY, P_YGP, P_YY,
                     PACK_LEN, check, dptr, lib)
 
 f64 = np.float64
@@ -302,7 +302,7 @@ class DeviceLineSearchContainer:
             check(lib().cgo_eval_trial_fused_dir(self.h, β, a, dptr(self._buf)))
             pk = self._buf.copy()
             self._cached = (a, pk)
-            self.dpack = np.array([pk[P_UG], pk[P_UU]])
+            self.dpack = np.array([pk[P_DIR_GU], pk[P_DIR_UU]])
         else:
             check(lib().cgo_update_dir(self.h, β, dptr(self._buf)))
             self.dpack = self._buf[:2].copy()

@@ -53,7 +53,12 @@ enum {
     CGO_P_YGP = 5,   /* y·g⁺                                              cg_flavours.jl:67,166 */
     CGO_P_GPG = 6,   /* g⁺·g                                              cg_flavours.jl:141 */
     CGO_P_UG = 7,    /* u·g   (= dϕ(0), nocedal.jl:56; cg_flavours.jl:145) */
-    CGO_P_UU = 8     /* u·u   (wolfe.jl:240, geometric.jl:52, cg_flavours.jl:65) */
+    CGO_P_UU = 8,    /* u·u   (cg_flavours.jl:65)                                              */
+    /* reduced by the BLAS-1 kernel that wrote u (the same numbers as slots 7/8 for one-kernel
+     * objectives; for CSR objectives a different canonical-order site):                       */
+    CGO_P_DIR_GU = 9,   /* g·u = dϕ(0) of the NEXT line search (nocedal.jl:56, wolfe.jl:40, geometric.jl:43) */
+    CGO_P_DIR_UU = 10,  /* u·u  (wolfe.jl:240, geometric.jl:52)                               */
+    CGO_P_XPXP = 11     /* xp·xp (ℓ2 regulariser of the logistic-regression objective)        */
 };
 /* pack written by cgo_update_dir / cgo_reset_direction / cgo_lbfgs_update_dir */
 enum { CGO_D_GU = 0 /* g·u, the next dϕ(0) */, CGO_D_UU = 1 /* u·u */ };
