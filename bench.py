@@ -42,7 +42,10 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="sparse_ls", choices=["sparse_ls", "rosenbrock"])
     p.add_argument("--n", type=int, default=0, help="problem size (default: BASELINE.json's)")
-    p.add_argument("--coh", type=int, default=0, help="sparse_ls generator: log2 rows sharing offsets")
+    p.add_argument("--coh", type=int, default=30,
+                   help="sparse_ls generator: log2 of the number of consecutive rows sharing their column "
+                        "offsets (30: ten true diagonals, SURVEY.md §8d cfg 3; 0: independent offsets per row)")
+    p.add_argument("--reduction-ctas", type=int, default=0, help="canonical-order G (0: library default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -128,14 +131,23 @@ def make_objective(cg, args, ctx, n):
     return obj, x0
 
 
+def matrix_bytes(n_local, nnz_local):
+    """one streaming pass over a CSR matrix: 8 B value + 4 B column index per entry + row pointers"""
+    return 12.0 * nnz_local + 8.0 * (n_local + 1)
+
+
 def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
-    """SURVEY.md §8(d) / DESIGN.md: algorithmic HBM bytes of `iters` iterations with `evals`
-    fdf! trials on one rank (fused minimum)."""
+    """Algorithmic HBM bytes of `iters` iterations with `evals` fdf! trials on
+    one rank: what the fused kernels must move when every vector is read / written once per kernel.
+    Rosenbrock: trial R x,g,u W xp,g⁺ = 40n, the first trial of an iteration also W u = 48n.
+    CSR least squares, per trial: K_a R x,u W xp = 24n | K_b A + gather xp 8n + R b 8n + W r 8n |
+    K_c Aᵀ + gather r 8n + R u,g 16n + W g⁺ 8n  = 2M + 80n; the first trial of an iteration also
+    R g, W u in K_a = +16n.  (SURVEY.md §8d's formula, (2M + 72n)·E + 48n, is larger: the β-dot
+    pass and the direction pass it counts separately are fused away here.)"""
     if args.workload == "rosenbrock":
-        # first trial of an iteration also applies updatedir!: R x,g,u W u,xp,g⁺ = 48n; later 40n
         return 8.0 * n_local * (6 * iters + 5 * (evals - iters))
-    per_eval = 2 * (12.0 * nnz_local + 8.0 * (n_local + 1)) + 72.0 * n_local
-    return evals * per_eval + 48.0 * n_local * iters
+    per_eval = 2 * matrix_bytes(n_local, nnz_local) + 80.0 * n_local
+    return evals * per_eval + 16.0 * n_local * iters
 
 
 def run_ours(args):
@@ -153,6 +165,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = cg.Context(local_rank)
+    if args.reduction_ctas:
+        ctx.set_reduction_ctas(args.reduction_ctas)
     if world > 1:
         ctx.comm_init_torch()
     n = args.n or FULL_N[args.workload]
@@ -209,11 +223,11 @@ def run_ours(args):
         dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
         dom_ms, dom_cnt = timers["trial"]
     else:
-        dom = "spmv+spmvT"
+        dom = "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)"
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]
         dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
-        # per SpMV launch: matrix (12 nnz + 8(n+1)) + gather 8n + R 8n (b / u) + W 8n  
-        dom_bytes = (dom_cnt / 2.0) * (2 * (12.0 * nnz_local + 8.0 * (n_local + 1)) + 48.0 * n_local)
+        # per launch pair: 2 x matrix stream + (gather 8n + R b 8n + W r 8n) + (gather 8n + R u,g 16n + W g+ 8n)
+        dom_bytes = (dom_cnt / 2.0) * (2 * matrix_bytes(n_local, nnz_local) + 56.0 * n_local)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     total_bytes = algorithmic_bytes(args, n_local, nnz_local, evals, K)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -254,8 +268,10 @@ def run_ours(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": (f"sparse least-squares 0.5||Ax-b||^2, CSR {n}x{n}, 10 nnz/row (banded-random, "
-                                    f"seed 24, coh_log2={args.coh}), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
+            "config": {"workload": (f"sparse least-squares 0.5||Ax-b||^2, CSR {n}x{n}, 10 nnz/row (banded, |col-row| < 2^20, "
+                                    f"seed 24, coh_log2={args.coh}: "
+                                    + ("ten diagonals" if args.coh >= 28 else "offsets redrawn every 2^%d rows" % args.coh)
+                                    + "), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
                                     if args.workload == "sparse_ls" else
                                     f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
                        "n": n, "sharding": f"rows/vector slices over {world} rank(s)",

@@ -49,6 +49,8 @@ _SIGS = {
     "cgo_comm_get_unique_id": (C.c_int, [_vp]),
     "cgo_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cgo_ctx_barrier": (C.c_int, [_vp]),
+    "cgo_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "cgo_host_free": (C.c_int, [_vp]),
     "cgo_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cgo_obj_rosenbrock_create": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "cgo_obj_sparse_ls_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(_vp)]),
@@ -100,6 +102,31 @@ def lib():
 def check(rc: int):
     if rc != 0:
         raise CgoError(f"libcgoptim error {rc}: {lib().cgo_last_error().decode(errors='replace')}")
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; freed when the last numpy view of it dies."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib().cgo_host_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p, nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().cgo_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(n: int) -> np.ndarray:
+    """float64 vector in page-locked host memory (device<->host copies run at PCIe speed)."""
+    blk = _PinnedBlock(8 * max(int(n), 1))
+    buf = (C.c_double * max(int(n), 1)).from_address(blk.ptr.value)
+    buf._cgo_owner = blk                   # the numpy array keeps `buf` (its base) alive, `buf` the block
+    return np.frombuffer(buf, dtype=np.float64, count=int(n))
 
 
 def dptr(a: np.ndarray):

@@ -154,6 +154,16 @@ extern "C" int cgo_ctx_comm_init(cgo_ctx *c, int nranks, int rank, const void *i
     return 0;
 }
 
+extern "C" int cgo_host_alloc(size_t bytes, void **out) {
+    CGO_CHECK(out != nullptr, "NULL argument");
+    CGO_CUDA(cudaHostAlloc(out, bytes > 0 ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int cgo_host_free(void *ptr) {
+    if (ptr) CGO_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
 extern "C" int cgo_shard_range(int64_t n, int nranks, int rank, int64_t align, int64_t *lo, int64_t *hi) {
     CGO_CHECK(lo && hi && nranks >= 1 && rank >= 0 && rank < nranks && align >= 1, "cgo_shard_range: bad arguments");
     int64_t units = n / align;

@@ -10,19 +10,18 @@
 // Aᵀ is an explicit CSR whose rows are sorted by source entry, so the gradient is a gather
 // (no atomics on data) and reproduces the sequential scatter order of the oracle bit for bit.
 //
-// k_csr_rows is a "CSR-stream" kernel: a CTA owns 256 consecutive rows; their nonzeros are one
-// contiguous range of val/col that the CTA streams with fully coalesced loads (10 independent
-// 12-byte loads per lane in flight), multiplies with the gathered vector entry and parks in
-// shared memory; lane t then adds up row t's products in storage order.  Rows of any length
-// work (the range is walked in chunks of 2560 entries).
+// k_csr_rows is a "CSR-stream" kernel: a CTA owns 256 consecutive rows at a time; their
+// nonzeros are one contiguous range of val/col, which a producer warp streams into a circular
+// shared-memory buffer with 1-D TMA bulk copies (cp.async.bulk + mbarrier, L2 evict-first) while
+// the 256 row lanes gather the vector entries and add up their row's products in storage
+// order.  Rows and tiles of any length work.
 #include <cub/device/device_scan.cuh>
 
 #include "internal.cuh"
 #include "reduce.cuh"
 
-constexpr int CSR_UN = 10;                  // entries per lane per chunk
-constexpr int CSR_CH = CGO_B * CSR_UN;      // entries per chunk (20 KB of products)
-constexpr int CSR_OCC = 4;
+
+constexpr int CSR_PAD = 16;                 // slack entries behind every CSR array (see csr_alloc)
 
 __device__ __forceinline__ double ld_stream_f64(const double *p) {
     double r;
@@ -38,69 +37,264 @@ __device__ __forceinline__ void st_stream_f64(double *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-// Canonical reduction site of these kernels: V = 1, U = 1 (item = row; include/cgoptim.h).
+// ------------------------------------------------------------------ mbarrier / TMA (1-D bulk) PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`; 16-byte
+// aligned addresses and size
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// ------------------------------------------------------------------ the CSR row kernel
+// Canonical reduction site: V = 1, U = 1 (item = row, lane t of a tile owns row t;
+// include/cgoptim.h).  Warp-specialised: warp 8 is the producer (one lane drives the TMA
+// engine), warps 0-7 are the 256 row lanes.  Everything that streams — matrix values, column
+// indices, row pointers and the epilogue's per-row operands (b; u, g; w) — reaches shared memory
+// only through bulk copies with an evict-first L2 policy; the lanes' only global loads are the
+// gathers of the vector, issued with an evict-last policy so that the gathered window stays in
+// L2 while the matrix streams through it.
+//
+// Shared-memory layout: a circular buffer of RING entries (values + column indices) that holds
+// variable-length chunks back to back, and TS_ND chunk descriptors (full/empty mbarrier pair,
+// the tile's row-pointer slice and operand slices).  A chunk is the entry range [p0 & ~3, p1)
+// of one tile (tiles of Aᵀ vary in length), or a CHMAX piece of it when the tile is longer than
+// half the ring.  The producer runs ahead as far as ring space and descriptors allow (about
+// three tiles); it reclaims space in FIFO order as the lanes release chunks.
+constexpr int TS_ND = 3;                    // chunk descriptors
+constexpr int TS_THREADS = CGO_B + 32;
+constexpr int TS_OCC = 2;
+constexpr int TS_UN = 10;                   // gathers in flight per lane
+constexpr int TS_SMEM_BUDGET = 115200;      // two CTAs per SM (228 KB - 2 x 1 KB reserved)
+template <int NOPS>
+struct TsLayout {
+    static constexpr int RP_BYTES = (CGO_B + 2) * 8;
+    static constexpr int OP_BYTES = CGO_B * 8;
+    static constexpr int DESC_BYTES = RP_BYTES + NOPS * OP_BYTES;
+    static constexpr int TAIL_BYTES = 2 * TS_ND * 8 + TS_ND * 4 + CGO_MAXK * CGO_NW * 8;
+    static constexpr int RING = ((TS_SMEM_BUDGET - TS_ND * DESC_BYTES - TAIL_BYTES - 64) / 12) & ~3;
+    static constexpr int CHMAX = (RING / 2) & ~3;
+    // byte offsets (all multiples of 16)
+    static constexpr int OFF_VAL = 0;
+    static constexpr int OFF_COL = OFF_VAL + RING * 8;
+    static constexpr int OFF_DESC = (OFF_COL + RING * 4 + 15) & ~15;
+    static constexpr int OFF_BAR = OFF_DESC + TS_ND * DESC_BYTES;
+    static constexpr int OFF_LEN = OFF_BAR + 2 * TS_ND * 8;
+    static constexpr int OFF_RED = (OFF_LEN + TS_ND * 4 + 15) & ~15;
+    static constexpr int BYTES = OFF_RED + CGO_MAXK * CGO_NW * 8;
+    static_assert(BYTES <= TS_SMEM_BUDGET && RP_BYTES % 16 == 0 && DESC_BYTES % 16 == 0, "smem layout");
+};
+
+__device__ __forceinline__ bool ts_next_tile(int &v, int64_t &tile, int nact, int64_t ntiles, int G) {
+    tile += G;
+    if (tile < ntiles) return true;
+    v += gridDim.x;
+    if (v >= nact) return false;
+    tile = v;
+    return true;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_gather_f64(const double *p, uint64_t pol) {
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
 template <class Epi>
-__global__ void __launch_bounds__(CGO_B, CSR_OCC)
+__global__ void __launch_bounds__(TS_THREADS, TS_OCC)
 k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
     constexpr int K = Epi::K;
-    __shared__ double prod[CSR_CH];
-    __shared__ double sm[K * CGO_NW];
-    __shared__ int64_t s_range[2];
+    constexpr int NOPS = Epi::NOPS;
+    using L = TsLayout<NOPS>;
+    constexpr int RING = L::RING, CHMAX = L::CHMAX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_val = reinterpret_cast<double *>(smem_raw + L::OFF_VAL);
+    int32_t *s_col = reinterpret_cast<int32_t *>(smem_raw + L::OFF_COL);
+    unsigned char *s_desc = smem_raw + L::OFF_DESC;
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR);
+    uint64_t *s_empty = s_full + TS_ND;
+    uint32_t *s_len = reinterpret_cast<uint32_t *>(smem_raw + L::OFF_LEN);   // producer's notes
+    double *s_red = reinterpret_cast<double *>(smem_raw + L::OFF_RED);
     const int tid = threadIdx.x;
     const int64_t nrows = A.nrows;
     const int64_t ntiles = (nrows + CGO_B - 1) / CGO_B;
     const int nact = (int)(ntiles < (int64_t)red.G ? ntiles : (int64_t)red.G);
+    if (tid == 0) {
+        for (int s = 0; s < TS_ND; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], CGO_NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= CGO_B) {                       // ---------------- producer warp
+        if (tid == CGO_B && (int)blockIdx.x < nact) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t c = 0, tail = 0;         // chunks issued / reclaimed
+            uint32_t head = 0, nfree = RING;
+            int v = blockIdx.x;
+            int64_t tile = v;
+            bool have = true;
+            int nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
+            int64_t p0n = __ldg(A.rowptr + tile * CGO_B), p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
+            while (have) {
+                const int64_t r0 = tile * CGO_B, p0 = p0n, p1 = p1n;
+                const int nvalid = nvalid_n;
+                have = ts_next_tile(v, tile, nact, ntiles, red.G);
+                if (have) {                   // row pointers of the next tile: in flight during this one
+                    nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
+                    p0n = __ldg(A.rowptr + tile * CGO_B);
+                    p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
+                }
+                bool first = true;
+                for (int64_t cs = p0 & ~(int64_t)3; first || cs < p1; cs += CHMAX) {
+                    const int64_t ce = cs + CHMAX < p1 ? cs + CHMAX : p1;
+                    const uint32_t cnt4 = p1 > p0 ? (uint32_t)((ce - cs + 3) & ~(int64_t)3) : 0u;
+                    // a free descriptor and cnt4 free ring entries: reclaim released chunks, oldest first
+                    while (tail + TS_ND <= c || nfree < cnt4) {
+                        mbar_wait(&s_empty[tail % TS_ND], (tail / TS_ND) & 1);
+                        nfree += s_len[tail % TS_ND];
+                        ++tail;
+                    }
+                    const int d = c % TS_ND;
+                    s_len[d] = cnt4;
+                    nfree -= cnt4;
+                    unsigned char *desc = s_desc + d * L::DESC_BYTES;
+                    const uint32_t rpb = first ? (uint32_t)((((nvalid + 1) * 8) + 15) & ~15) : 0u;
+                    const uint32_t opb = first ? (uint32_t)(((nvalid * 8) + 15) & ~15) : 0u;
+                    mbar_expect_tx(&s_full[d], cnt4 * 12u + rpb + NOPS * opb);
+                    if (first) {
+                        tma_load_1d(desc, A.rowptr + r0, rpb, &s_full[d], pol);
+#pragma unroll
+                        for (int o = 0; o < NOPS; ++o)
+                            tma_load_1d(desc + L::RP_BYTES + o * L::OP_BYTES, epi.operand(o) + r0, opb, &s_full[d], pol);
+                    }
+                    if (cnt4) {
+                        const uint32_t n1 = cnt4 < RING - head ? cnt4 : RING - head;   // up to the ring's end
+                        tma_load_1d(s_val + head, A.val + cs, n1 * 8u, &s_full[d], pol);
+                        tma_load_1d(s_col + head, A.col + cs, n1 * 4u, &s_full[d], pol);
+                        if (n1 < cnt4) {                                               // wrapped remainder
+                            tma_load_1d(s_val, A.val + cs + n1, (cnt4 - n1) * 8u, &s_full[d], pol);
+                            tma_load_1d(s_col, A.col + cs + n1, (cnt4 - n1) * 4u, &s_full[d], pol);
+                        }
+                        head += cnt4;
+                        if (head >= RING) head -= RING;
+                    }
+                    first = false;
+                    ++c;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- 256 row lanes
+    const BarLanes bar;
+    const uint64_t gpol = l2_policy_evict_last();
+    uint32_t c = 0, head = 0;                 // chunks consumed, ring offset of the next chunk
     for (int v = blockIdx.x; v < nact; v += gridDim.x) {
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
         for (int64_t tile = v; tile < ntiles; tile += red.G) {
-            const int64_t row = tile * CGO_B + tid;
-            const bool valid = row < nrows;
-            int64_t rs = 0, re = 0;
-            if (valid) { rs = __ldg(A.rowptr + row); re = __ldg(A.rowptr + row + 1); }
-            if (tid == 0) s_range[0] = rs;
-            if (valid && (tid == CGO_B - 1 || row == nrows - 1)) s_range[1] = re;
-            __syncthreads();
-            const int64_t p0 = s_range[0], p1 = s_range[1];
+            const int64_t r0 = tile * CGO_B;
+            const int nvalid = (int)(nrows - r0 < CGO_B ? nrows - r0 : CGO_B);
+            const bool valid = tid < nvalid;
+            typename Epi::Pre pre;
+            int64_t rs = 0, re = 0, p0 = 0, p1 = 0, cs = 0;
             double sum = 0.0;
-            for (int64_t c0 = p0; c0 < p1; c0 += CSR_CH) {
-                int32_t cj[CSR_UN];
-                double vj[CSR_UN];
-#pragma unroll
-                for (int j = 0; j < CSR_UN; ++j) {
-                    const int64_t p = c0 + tid + j * CGO_B;
-                    if (p < p1) { cj[j] = ld_stream_s32(A.col + p); vj[j] = ld_stream_f64(A.val + p); }
+            bool first = true;
+            do {
+                const int d = c % TS_ND;
+                mbar_wait(&s_full[d], (c / TS_ND) & 1);
+                if (first) {
+                    const unsigned char *desc = s_desc + d * L::DESC_BYTES;
+                    const int64_t *rp = reinterpret_cast<const int64_t *>(desc);
+                    if (valid) {
+                        rs = rp[tid]; re = rp[tid + 1];
+                        pre = epi.load(reinterpret_cast<const double *>(desc + L::RP_BYTES), tid);
+                    }
+                    p0 = rp[0];
+                    p1 = rp[nvalid];
+                    cs = p0 & ~(int64_t)3;
+                    first = false;
                 }
+                const int64_t ce = cs + CHMAX < p1 ? cs + CHMAX : p1;
+                const uint32_t cnt4 = p1 > p0 ? (uint32_t)((ce - cs + 3) & ~(int64_t)3) : 0u;
+                const int lo = (int)((rs > cs ? rs : cs) - cs);
+                const int hi = (int)((re < ce ? re : ce) - cs);
+                for (int k0 = lo; k0 < hi; k0 += TS_UN) {
+                    // branch-free batch: TS_UN gathers are issued back to back (entries past the
+                    // row's end re-read its last entry and are not added)
+                    double vj[TS_UN], xj[TS_UN];
 #pragma unroll
-                for (int j = 0; j < CSR_UN; ++j) {
-                    const int64_t p = c0 + tid + j * CGO_B;
-                    if (p < p1) prod[tid + j * CGO_B] = vj[j] * __ldg(xg + cj[j]);
+                    for (int j = 0; j < TS_UN; ++j) {
+                        const int kk = k0 + j < hi ? k0 + j : hi - 1;
+                        uint32_t idx = head + (uint32_t)kk;
+                        if (idx >= RING) idx -= RING;
+                        vj[j] = s_val[idx];
+                        xj[j] = ld_gather_f64(xg + s_col[idx], gpol);
+                    }
+#pragma unroll
+                    for (int j = 0; j < TS_UN; ++j) {
+                        const double t = sum + vj[j] * xj[j];
+                        sum = k0 + j < hi ? t : sum;
+                    }
                 }
-                __syncthreads();
-                int64_t lo = rs > c0 ? rs : c0;
-                int64_t hi = re < c0 + CSR_CH ? re : c0 + CSR_CH;
-                for (int64_t p = lo; p < hi; ++p) sum = sum + prod[p - c0];
-                __syncthreads();
-            }
-            if (valid) epi.row(row, sum, acc);
-            __syncthreads();      // s_range is rewritten by the next tile
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&s_empty[d]);
+                head += cnt4;
+                if (head >= RING) head -= RING;
+                ++c;
+                cs += CHMAX;
+            } while (cs < p1);
+            if (valid) epi.row(r0 + tid, sum, pre, acc);
         }
-        cgo_cta_combine<K>(acc, sm);
+        cgo_cta_combine<K, BarLanes>(acc, s_red, bar);
         cgo_publish<K>(red, v, acc);
     }
-    cgo_grid_finish<K>(red, nact, sm);
+    cgo_grid_finish<K, BarLanes>(red, nact, s_red, bar);
 }
 
 template <class Epi>
 static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
     const int64_t ntiles = (A.nrows + CGO_B - 1) / CGO_B;
     int64_t nact = ntiles < red.G ? ntiles : red.G;
-    int64_t phys = (int64_t)c->sms * CSR_OCC;
+    int64_t phys = (int64_t)c->sms * TS_OCC;
     int grid = (int)(nact < phys ? nact : phys);
     if (grid < 1) grid = 1;
+    const size_t smem = TsLayout<Epi::NOPS>::BYTES;
+    CGO_CUDA(cudaFuncSetAttribute(k_csr_rows<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cgo_timer_begin(c, tclass);
-    k_csr_rows<Epi><<<grid, CGO_B, 0, c->stream>>>(A, xg, epi, red);
+    k_csr_rows<Epi><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red);
     cgo_timer_end(c);
     c->launches++;
     CGO_CUDA(cudaGetLastError());
@@ -108,17 +302,27 @@ static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &
 }
 
 // ------------------------------------------------------------------ row epilogues
+// operand(o): per-row input vectors of the epilogue; the producer stages the tile's slice of
+// each in shared memory next to the row pointers (they must be 16-byte aligned and padded by
+// one element).  load() picks lane t's values out of that slice; row() consumes them once the
+// row sum is known.
 struct EpiStore {                       // y = A x
-    static constexpr int K = 1;
+    static constexpr int K = 1, NOPS = 0;
+    struct Pre {};
     double *y;
-    __device__ __forceinline__ void row(int64_t i, double sum, double (&)[K]) const { y[i] = sum; }
+    __device__ __forceinline__ const double *operand(int) const { return nullptr; }
+    __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
+    __device__ __forceinline__ void row(int64_t i, double sum, const Pre &, double (&)[K]) const { y[i] = sum; }
 };
 struct EpiResidual {                    // r = A xp − b ; Σ r²
-    static constexpr int K = 1;
+    static constexpr int K = 1, NOPS = 1;
+    struct Pre { double b; };
     const double *b;
     double *r;
-    __device__ __forceinline__ void row(int64_t i, double sum, double (&acc)[K]) const {
-        const double rr = sum - ld_stream_f64(b + i);
+    __device__ __forceinline__ const double *operand(int) const { return b; }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const { return Pre{ops[t]}; }
+    __device__ __forceinline__ void row(int64_t i, double sum, const Pre &p, double (&acc)[K]) const {
+        const double rr = sum - p.b;
         r[i] = rr;                      // re-read (gathered) by K_c: keep it cacheable
         acc[0] = acc[0] + rr * rr;
     }
@@ -127,15 +331,23 @@ struct EpiResidual {                    // r = A xp − b ; Σ r²
 // the getβ dots (cg_flavours.jl:63-76, 96-105, 140-145, 164-167); fills pack slots 1..8.
 template <bool LOGREG>
 struct EpiGrad {
-    static constexpr int K = 8;
+    static constexpr int K = 8, NOPS = LOGREG ? 3 : 2;
+    struct Pre { double u, g, w; };
     double *gp;
     const double *g, *u, *w;
     double invN, lambda;
-    __device__ __forceinline__ void row(int64_t j, double sum, double (&acc)[K]) const {
+    __device__ __forceinline__ const double *operand(int o) const { return o == 0 ? u : (o == 1 ? g : w); }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const {
+        Pre p;
+        p.u = ops[t]; p.g = ops[CGO_B + t];
+        p.w = LOGREG ? ops[2 * CGO_B + t] : 0.0;
+        return p;
+    }
+    __device__ __forceinline__ void row(int64_t j, double sum, const Pre &p, double (&acc)[K]) const {
         double gn = sum;
-        if (LOGREG) gn = sum * invN + lambda * ld_stream_f64(w + j);
+        if (LOGREG) gn = sum * invN + lambda * p.w;
         st_stream_f64(gp + j, gn);
-        const double uu = ld_stream_f64(u + j), gg = ld_stream_f64(g + j);
+        const double uu = p.u, gg = p.g;
         const double y = gn - gg;
         acc[CGO_P_DPHI - 1] = acc[CGO_P_DPHI - 1] + gn * uu;
         acc[CGO_P_GPGP - 1] = acc[CGO_P_GPGP - 1] + gn * gn;
@@ -150,11 +362,14 @@ struct EpiGrad {
 // logistic loss of sample i with margin z = a_i·w (oracle logreg_fdf):
 //   t = −y z; e = exp(−|t|); ℓ = max(t,0) + log1p(e); σ = t ≥ 0 ? 1/(1+e) : e/(1+e); c = −y σ
 struct EpiLogit {
-    static constexpr int K = 1;
+    static constexpr int K = 1, NOPS = 1;
+    struct Pre { double y; };
     const double *label;
     double *c;
-    __device__ __forceinline__ void row(int64_t i, double z, double (&acc)[K]) const {
-        const double y = ld_stream_f64(label + i);
+    __device__ __forceinline__ const double *operand(int) const { return label; }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const { return Pre{ops[t]}; }
+    __device__ __forceinline__ void row(int64_t i, double z, const Pre &p, double (&acc)[K]) const {
+        const double y = p.y;
         const double t = -y * z;
         const double e = exp(-fabs(t));
         const double l = (t > 0.0 ? t : 0.0) + log1p(e);
@@ -393,9 +608,10 @@ static void csr_free(CsrMat &M) {
 }
 static int csr_alloc(CsrMat &M, int64_t nrows, int64_t nnz) {
     M.nrows = nrows; M.nnz = nnz;
-    CGO_CUDA(cudaMalloc(&M.rowptr, sizeof(int64_t) * (size_t)(nrows + 1)));
-    CGO_CUDA(cudaMalloc(&M.col, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-    CGO_CUDA(cudaMalloc(&M.val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    // CSR_PAD: bulk copies are rounded up to 16 bytes and may read past the last entry
+    CGO_CUDA(cudaMalloc(&M.rowptr, sizeof(int64_t) * (size_t)(nrows + 1 + CSR_PAD)));
+    CGO_CUDA(cudaMalloc(&M.col, sizeof(int32_t) * (size_t)(nnz + CSR_PAD)));
+    CGO_CUDA(cudaMalloc(&M.val, sizeof(double) * (size_t)(nnz + CSR_PAD)));
     return 0;
 }
 
@@ -412,7 +628,7 @@ static int build_transpose(cgo_ctx *c, const Src &src, const Fin &fin, int64_t n
         if (src.total > 0) k_tr_count<<<grid_for(src.total, c->sms), 256, 0, s>>>(src, counts);
         CGO_CUDA(cudaGetLastError());
         AT.nrows = nT;
-        CGO_CUDA(cudaMalloc(&AT.rowptr, sizeof(int64_t) * (size_t)(nT + 1)));
+        CGO_CUDA(cudaMalloc(&AT.rowptr, sizeof(int64_t) * (size_t)(nT + 1 + CSR_PAD)));
         size_t tmp_bytes = 0;
         CGO_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int64_t *)counts, AT.rowptr, nT + 1, s));
         CGO_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
@@ -430,8 +646,8 @@ static int build_transpose(cgo_ctx *c, const Src &src, const Fin &fin, int64_t n
         CGO_CUDA(cudaGetLastError());
         if (nT > 0) k_tr_sort<<<grid_for(nT, c->sms), 256, 0, s>>>(AT.rowptr, nT, perm);
         CGO_CUDA(cudaGetLastError());
-        CGO_CUDA(cudaMalloc(&AT.col, sizeof(int32_t) * (size_t)(nnzT > 0 ? nnzT : 1)));
-        CGO_CUDA(cudaMalloc(&AT.val, sizeof(double) * (size_t)(nnzT > 0 ? nnzT : 1)));
+        CGO_CUDA(cudaMalloc(&AT.col, sizeof(int32_t) * (size_t)(nnzT + CSR_PAD)));
+        CGO_CUDA(cudaMalloc(&AT.val, sizeof(double) * (size_t)(nnzT + CSR_PAD)));
         if (nnzT > 0) k_tr_finalize<<<grid_for(nnzT, c->sms), 256, 0, s>>>(fin, nnzT, perm, AT);
         CGO_CUDA(cudaGetLastError());
         CGO_CUDA(cudaStreamSynchronize(s));
@@ -542,7 +758,7 @@ extern "C" int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n, int32
         CGO_CUDA(cudaMalloc(&xt_base, sizeof(double) * (size_t)(nloc + 2 * o->halo)));
         k_ls_xtrue<<<grid_for(nloc + 2 * o->halo, ctx->sms), 256, 0, ctx->stream>>>(sp, lo, nloc, o->halo, xt_base + o->halo);
         CGO_CUDA(cudaGetLastError());
-        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)nloc));
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(nloc + CSR_PAD)));
         EpiStore es{o->b};
         CGO_TRY(launch_csr(ctx, o->A, xt_base + o->halo, es, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_OTHER));
         CGO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -588,7 +804,7 @@ extern "C" int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t
             CGO_CUDA(cudaMemcpyAsync(o->A.col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
             CGO_CUDA(cudaMemcpyAsync(o->A.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s));
         }
-        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)nrows));
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(nrows + CSR_PAD)));
         CGO_CUDA(cudaMemcpyAsync(o->b, b, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, s));
         CGO_TRY(o->alloc_r());
         CsrSrc src{o->A.col, nnz};
@@ -616,7 +832,7 @@ extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t 
     auto body = [&]() -> int {
         CGO_TRY(check_i32(N > d ? N : d, "matrix dimension"));
         CGO_TRY(csr_alloc(o->A, N, N * K));
-        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)N));
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(N + CSR_PAD)));
         k_lr_fill_A<<<grid_for(N, ctx->sms), 256, 0, ctx->stream>>>(sp, o->A, o->b);
         CGO_CUDA(cudaGetLastError());
         CGO_TRY(o->alloc_r());

@@ -56,7 +56,7 @@ struct cgo_ctx {
     int sms = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int G = 1184;
+    int G = 296;
     int64_t launches = 0;
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax

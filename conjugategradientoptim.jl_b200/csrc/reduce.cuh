@@ -8,9 +8,16 @@
 #pragma once
 #include "internal.cuh"
 
+// CTA-wide barrier over the CGO_B reducing lanes.  BarAll: the whole CTA reduces.  BarLanes:
+// only threads [0, CGO_B) do (warp-specialised kernels keep their producer warp out of it).
+struct BarAll { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct BarLanes {
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, %0;" ::"n"(CGO_B) : "memory"); }
+};
+
 // Combine the CGO_B lanes of a CTA.  Result valid in thread 0 (acc[] of thread 0).
-template <int K>
-__device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* K*CGO_NW */) {
+template <int K, class Bar = BarAll>
+__device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* K*CGO_NW */, Bar bar = Bar()) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -19,7 +26,7 @@ __device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* 
         for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) sm[k * CGO_NW + warp] = v;
     }
-    __syncthreads();
+    bar();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -29,7 +36,7 @@ __device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* 
             acc[k] = s;
         }
     }
-    __syncthreads();
+    bar();
 }
 
 // Thread 0 of virtual CTA `vcta` publishes its K partials.
@@ -43,16 +50,16 @@ __device__ __forceinline__ void cgo_publish(const RedArgs &red, int vcta, const 
 
 // Called by every physical CTA once all its virtual CTAs are published.  The last CTA to arrive
 // combines the `nact` partials in canonical order and writes red.out[0..K).
-template <int K>
-__device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, double *sm) {
+template <int K, class Bar = BarAll>
+__device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, double *sm, Bar bar = Bar()) {
     __shared__ bool is_last;
     __threadfence();
-    __syncthreads();
+    bar();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(red.ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
-    __syncthreads();
+    bar();
     if (!is_last) return;
     __threadfence();
     double acc[K];
@@ -62,7 +69,7 @@ __device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, do
         for (int c = threadIdx.x; c < nact; c += CGO_B) s = s + __ldcg(&red.partial[(size_t)k * red.G + c]);
         acc[k] = s;
     }
-    cgo_cta_combine<K>(acc, sm);
+    cgo_cta_combine<K, Bar>(acc, sm, bar);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) red.out[k] = acc[k];

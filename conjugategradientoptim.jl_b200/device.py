@@ -145,12 +145,14 @@ class DeviceObjective:
 
     # CSR test hooks
     def csr(self, transposed=False):
-        nr, nnz = C.c_int64(), C.c_int64()
+        """(rowptr, col, val, b) of A, or of the explicit transpose; b always has A's row count."""
+        nr, nnz, nra = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib().cgo_obj_csr_nnz(self.h, int(transposed), C.byref(nr), C.byref(nnz)))
+        check(lib().cgo_obj_csr_nnz(self.h, 0, C.byref(nra), None))
         rp = np.empty(nr.value + 1, dtype=np.int64)
         ci = np.empty(nnz.value, dtype=np.int32)
         va = np.empty(nnz.value)
-        b = np.empty(nr.value)
+        b = np.empty(nra.value)
         check(lib().cgo_obj_csr_download(self.h, int(transposed), rp.ctypes.data, ci.ctypes.data,
                                          va.ctypes.data, b.ctypes.data))
         return rp, ci, va, b
@@ -368,7 +370,7 @@ class DeviceLineSearchContainer:
 
     # -- results ---------------------------------------------------------------------
     def download(self):
-        x, g = np.empty(self.n), np.empty(self.n)
+        x, g = capi.pinned_empty(self.n), capi.pinned_empty(self.n)
         check(lib().cgo_download(self.h, dptr(x), dptr(g)))
         return x, g
 

@@ -25,12 +25,14 @@
  *   +0.0; the 256 lanes of a virtual CTA are combined by a xor-butterfly (16,8,4,2,1) inside
  *   each warp, then sequentially over the 8 warps; the min(G, ntiles) CTA partials are combined
  *   by the last-arriving block in exactly the same way (lane t takes partials t, t+256, ...).
- *   G defaults to 1184 (= 148 SMs x 8) and is a property of the ctx.  With R ranks every rank
+ *   G defaults to 296 (= 2 persistent CTAs on each of a B200's 148 SMs, whatever the device: one
+ *   sweep over the data by the whole grid) and is a property of the ctx.  With R ranks every rank
  *   reduces its contiguous shard this way; the R shard results are all-gathered and added in
  *   rank order on every rank.
  */
 #ifndef CGOPTIM_H
 #define CGOPTIM_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -81,7 +83,7 @@ int cgo_version(void);
 int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out);
 int cgo_ctx_destroy(cgo_ctx *ctx);
 int cgo_ctx_stream(cgo_ctx *ctx, void **cuda_stream_out);
-int cgo_ctx_set_reduction_ctas(cgo_ctx *ctx, int G);        /* canonical-order G (default 1184) */
+int cgo_ctx_set_reduction_ctas(cgo_ctx *ctx, int G);        /* canonical-order G (default 296) */
 int cgo_ctx_sm_count(cgo_ctx *ctx, int *sms);
 int cgo_ctx_kernel_launches(cgo_ctx *ctx, int64_t *count);  /* kernels launched so far */
 /* optional per-launch CUDA-event timing on the ctx stream, by kernel class:
@@ -93,6 +95,10 @@ int cgo_ctx_timing_read(cgo_ctx *ctx, double ms[8], int64_t counts[8], int reset
 int cgo_comm_get_unique_id(void *id128);
 int cgo_ctx_comm_init(cgo_ctx *ctx, int nranks, int rank, const void *id128);
 int cgo_ctx_barrier(cgo_ctx *ctx);
+/* page-locked host memory (Results.minimizer / Results.gradient land in it at PCIe speed; x_initial
+ * may live in it too).  Plain pageable pointers are accepted everywhere, just slower. */
+int cgo_host_alloc(size_t bytes, void **out);
+int cgo_host_free(void *ptr);
 /* contiguous shard [lo,hi) of n items for `rank` of `nranks`, boundaries multiples of `align` */
 int cgo_shard_range(int64_t n, int nranks, int rank, int64_t align, int64_t *lo, int64_t *hi);
 

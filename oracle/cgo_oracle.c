@@ -78,8 +78,8 @@ static double dot_comp(const double *a, const double *b, int64_t n) { /* Neumaie
  * same way (lane t takes partials t, t+B, ...).  Shards (ranks) each reduce their contiguous
  * slice this way and the shard results are added in rank order.                            */
 enum { CGO_B = 256 };
-static int g_cgo_G = 1184, g_cgo_shards = 1;
-void orc_set_cgo_order(int G, int shards) { g_cgo_G = G > 0 ? G : 1184; g_cgo_shards = shards > 0 ? shards : 1; }
+static int g_cgo_G = 296, g_cgo_shards = 1;
+void orc_set_cgo_order(int G, int shards) { g_cgo_G = G > 0 ? G : 296; g_cgo_shards = shards > 0 ? shards : 1; }
 static double cgo_cta_combine(double *lane /* CGO_B, clobbered */) {
     double wsum[CGO_B / 32];
     for (int w = 0; w < CGO_B / 32; ++w) {

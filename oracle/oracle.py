@@ -218,6 +218,8 @@ class Objective:
         fr, fc, fv = ((L.orc_csrT_rowptr, L.orc_csrT_col, L.orc_csrT_val) if transposed
                       else (L.orc_csr_rowptr, L.orc_csr_col, L.orc_csr_val))
         rp = np.ctypeslib.as_array(C.cast(fr(self.h), C.POINTER(C.c_int64)), (nrows + 1,)).copy()
+        if nnz == 0:
+            return rp, np.zeros(0, dtype=np.int32), np.zeros(0)
         ci = np.ctypeslib.as_array(C.cast(fc(self.h), C.POINTER(C.c_int32)), (nnz,)).copy()
         va = np.ctypeslib.as_array(C.cast(fv(self.h), C.POINTER(C.c_double)), (nnz,)).copy()
         return rp, ci, va
@@ -241,7 +243,7 @@ def dot(a, b, sum_mode="seq", threads=1):
     return lib().orc_dot(_dp(a), _dp(b), a.size, SUM_MODES[sum_mode], threads)
 
 
-def set_cgo_order(G=1184, shards=1):
+def set_cgo_order(G=296, shards=1):
     """Parameters of the canonical reduction order (include/cgoptim.h): virtual CTAs, shards."""
     lib().orc_set_cgo_order(G, shards)
 

@@ -23,7 +23,7 @@ def ctx():
 
 
 @pytest.mark.parametrize("n", [2, 4, 10, 2048, 2050, 4096 + 6, 100_000, 1_000_002])
-@pytest.mark.parametrize("G", [1184, 3])
+@pytest.mark.parametrize("G", [296, 1184, 3])
 def test_trial_pack_bit_exact(ctx, n, G):
     """cgo_eval_trial pack == oracle fdf + canonical-order dots (evalϕdϕ!, cg_utils.jl:3-22)."""
     ctx.set_reduction_ctas(G)
@@ -58,8 +58,8 @@ def test_trial_pack_bit_exact(ctx, n, G):
         assert ws.norm_u_plus_g() == 0.0
         ws.close()
     finally:
-        ctx.set_reduction_ctas(1184)
-        O.set_cgo_order(1184, 1)
+        ctx.set_reduction_ctas(296)
+        O.set_cgo_order(296, 1)
 
 
 def test_fused_direction_equals_unfused(ctx):

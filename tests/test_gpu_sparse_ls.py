@@ -100,7 +100,7 @@ def test_from_csr_rejects_bad_input(ctx):
         cg.SparseLSGPU_from_csr(10, 10, rp2, col, val, b, ctx)
 
 
-@pytest.mark.parametrize("n,G", [(3000, 1184), (3000, 3), (100_000, 1184), (400_000, 7)])
+@pytest.mark.parametrize("n,G", [(3000, 296), (3000, 3), (100_000, 1184), (400_000, 7)])
 def test_trial_pack_bit_exact(ctx, n, G):
     """evalϕdϕ! (cg_utils.jl:3-22) on the CSR objective == oracle fdf + canonical-order dots."""
     ctx.set_reduction_ctas(G)
@@ -125,8 +125,8 @@ def test_trial_pack_bit_exact(ctx, n, G):
         ws.close()
         obj.close()
     finally:
-        ctx.set_reduction_ctas(1184)
-        O.set_cgo_order(1184, 1)
+        ctx.set_reduction_ctas(296)
+        O.set_cgo_order(296, 1)
 
 
 @pytest.mark.parametrize("flavour", FLAVOURS)
