@@ -105,17 +105,32 @@ def check(rc: int):
 
 
 class _PinnedBlock:
-    """Owner of one cudaHostAlloc block; freed when the last numpy view of it dies."""
+    """Owner of one cudaHostAlloc block.  Page-locking is slow (~1 s per GB), so a block whose
+    last numpy view died goes back to a small free list and is handed out again by the next
+    `pinned_empty` of the same size (Results of successive runs reuse the same host pages)."""
+    POOL: dict = {}                  # nbytes -> [ptr, ...]
+    POOL_BYTES = 0
+    POOL_CAP = 16 << 30              # retained bytes; beyond it blocks are freed
 
     def __init__(self, nbytes: int):
-        p = C.c_void_p()
-        check(lib().cgo_host_alloc(nbytes, C.byref(p)))
-        self.ptr, self.nbytes = p, nbytes
+        free = _PinnedBlock.POOL.get(nbytes)
+        if free:
+            self.ptr = free.pop()
+            _PinnedBlock.POOL_BYTES -= nbytes
+        else:
+            p = C.c_void_p()
+            check(lib().cgo_host_alloc(nbytes, C.byref(p)))
+            self.ptr = p
+        self.nbytes = nbytes
 
     def __del__(self):
         try:
             if self.ptr:
-                lib().cgo_host_free(self.ptr)
+                if _PinnedBlock.POOL_BYTES + self.nbytes <= _PinnedBlock.POOL_CAP:
+                    _PinnedBlock.POOL.setdefault(self.nbytes, []).append(self.ptr)
+                    _PinnedBlock.POOL_BYTES += self.nbytes
+                else:
+                    lib().cgo_host_free(self.ptr)
                 self.ptr = None
         except Exception:
             pass
@@ -127,6 +142,15 @@ def pinned_empty(n: int) -> np.ndarray:
     buf = (C.c_double * max(int(n), 1)).from_address(blk.ptr.value)
     buf._cgo_owner = blk                   # the numpy array keeps `buf` (its base) alive, `buf` the block
     return np.frombuffer(buf, dtype=np.float64, count=int(n))
+
+
+def pinned_pool_clear():
+    """Free every retained page-locked block."""
+    for ptrs in _PinnedBlock.POOL.values():
+        for p in ptrs:
+            lib().cgo_host_free(p)
+    _PinnedBlock.POOL.clear()
+    _PinnedBlock.POOL_BYTES = 0
 
 
 def dptr(a: np.ndarray):

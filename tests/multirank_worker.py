@@ -1,0 +1,70 @@
+"""Worker of tests/test_gpu_multirank.py: one process per GPU (torchrun), rows / vector slices
+sharded over the ranks, compared bit for bit with the oracle run on the WHOLE problem in
+canonical order with the same shard count (include/cgoptim.h: every rank reduces its shard, the
+shard results are added in rank order)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cgoptim_b200 as cg  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from helpers import make_pair  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = cg.Context(local)
+    ctx.comm_init_torch()
+    O.set_cgo_order(296, world)
+    fails = []
+
+    def check(name, obj, x0_full, ora_obj, flavour, max_iters):
+        ocfg, cfg, ls = make_pair(flavour, max_iters=max_iters)
+        lo, hi = obj.offset, obj.offset + obj.n_local
+        assert (lo, hi) == cg.shard_range(obj.n_global, world, rank, 2)
+        ret = cg.minimizeobjective(obj, x0_full[lo:hi], cfg, ls)
+        ora = O.minimize(ora_obj, x0_full, ocfg)
+        ok = (ret.status == ora.status and ret.iters_ran == ora.iters_ran
+              and np.array_equal(ret.trace.objective, ora.trace_objective)
+              and np.array_equal(ret.trace.grad_norm, ora.trace_grad_norm)
+              and np.array_equal(ret.trace.step_size, ora.trace_step_size)
+              and np.array_equal(ret.trace.objective_evals, ora.trace_objective_evals)
+              and np.array_equal(ret.minimizer, ora.minimizer[lo:hi])
+              and np.array_equal(ret.gradient, ora.gradient[lo:hi]))
+        if not ok:
+            fails.append(f"{name}/{flavour}: rank {rank} status {ret.status}/{ora.status} iters {ret.iters_ran}/{ora.iters_ran} "
+                         f"f {ret.objective!r}/{ora.objective!r}")
+
+    n = 40_000
+    for flavour in ("HagerZhang", "LBFGS"):
+        obj = cg.RosenbrockGPU(n, ctx)
+        check("rosenbrock", obj, O.rosenbrock_x0(n, 24, 0.1), O.Objective.rosenbrock(n), flavour, 40)
+        obj.close()
+    for coh in (0, 30):
+        for flavour in ("HagerZhang", "LBFGS"):
+            obj = cg.SparseLSGPU(n, 10, 2048, 24, coh, ctx)
+            check(f"sparse_ls coh={coh}", obj, np.zeros(n), O.Objective.sparse_ls(n, 10, 2048, 24, coh), flavour, 60)
+            obj.close()
+    ctx.barrier()
+    t = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(t)
+    for f in fails:
+        print("MISMATCH", f, flush=True)
+    if rank == 0:
+        print("MULTIRANK_OK" if int(t.item()) == 0 else f"MULTIRANK_FAILED {int(t.item())}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
