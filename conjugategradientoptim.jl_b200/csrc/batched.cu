@@ -1,0 +1,365 @@
+// batched.cu — many independent small problems, the whole solver on the device
+// (BASELINE.json configs[4]; SURVEY.md §8 cfg 5).
+//
+// One CTA of 256 lanes per problem.  The host cannot drive hundreds of thousands of divergent
+// line-search state machines, so this file restates on the device, scalar for scalar:
+//   minimizeobjective          src/engine/optim.jl:6-171
+//   linesearch! / zoom!        src/linesearch/nocedal.jl:33-209   (StrongWolfeBisection)
+//   getβ                       src/cg_flavours.jl:51-79 (YuanWangSheng), :87-108 (HagerZhang),
+//                              :133-151 (SallehAlhawarat), :157-170 (LiuStorrey)
+//   updatedir!, initializeLineSearchContainer!   src/cg_flavours.jl:2-35
+//   evalϕdϕ!                   src/cg_utils.jl:3-22, objective = extended Rosenbrock
+// Every lane runs the same scalar state machine on identical reduced scalars (uniform control
+// flow, no divergence inside a problem).  Lane t owns the elements {2q, 2q+1 : q = t + 256 j},
+// i.e. exactly the canonical-order mapping (V = 2, U = 4, one tile) of include/cgoptim.h, so the
+// five n-vectors x, g, u, xp, g⁺ live in REGISTERS and each dot product is the canonical
+// butterfly + warp-ordered sum: results are bit-identical to the oracle run problem by problem
+// (ORC_SUM_CGO, ORC_BETA_FUSED) and to the single-problem device path.  No HBM traffic between
+// reading x0 and writing the result: the roofline that binds is on-chip latency, not HBM.
+#include <math.h>
+
+#include "internal.cuh"
+
+namespace {
+
+constexpr int BT = CGO_B;              // lanes per problem
+constexpr int NW = CGO_NW;
+
+struct Pack9 { double v[9]; };
+
+// canonical CTA combine, result broadcast to every lane (double-buffered scratch: one barrier)
+template <int K>
+__device__ __forceinline__ void cta_allreduce(double (&acc)[K], double *scratch /* 2 * K * NW */, int &phase) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sm = scratch + phase * (K * NW);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[k * NW + warp] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = sm[k * NW];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) s = s + sm[k * NW + w];
+        acc[k] = s;
+    }
+    phase ^= 1;
+}
+
+__device__ __forceinline__ double jl_max(double a, double b) {     // Julia max: NaN-propagating
+    if (a != a) return a;
+    if (b != b) return b;
+    return a > b ? a : b;
+}
+
+template <int NPT>
+struct Problem {
+    double2 x[NPT], g[NPT], u[NPT], xp[NPT], gp[NPT];
+    int n;                              // problem dimension (even)
+    double *scratch;
+    int phase;
+    int64_t evals;
+
+    __device__ __forceinline__ bool owns(int j) const { return 2 * (threadIdx.x + j * BT) < n; }
+
+    // f, g at x (optim.jl:25): returns f and ‖g‖²
+    __device__ __forceinline__ void eval_initial(double &f, double &gg) {
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (owns(j)) {
+                const double t = x[j].y - x[j].x * x[j].x;
+                const double om = 1.0 - x[j].x;
+                g[j].x = (-400.0 * x[j].x) * t - 2.0 * om;
+                g[j].y = 200.0 * t;
+                acc[0] = acc[0] + ((100.0 * t) * t + om * om);
+                acc[1] = acc[1] + g[j].x * g[j].x;
+                acc[1] = acc[1] + g[j].y * g[j].y;
+            }
+        }
+        cta_allreduce<2>(acc, scratch, phase);
+        f = acc[0]; gg = acc[1];
+        evals++;
+    }
+    // u = −g + βu (reset: u = −g); returns g·u  (cg_flavours.jl:10-12, :28; nocedal.jl:56)
+    __device__ __forceinline__ double update_dir(double beta, bool reset) {
+        double acc[1] = {0.0};
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (owns(j)) {
+                if (reset) { u[j].x = -g[j].x; u[j].y = -g[j].y; }
+                else { u[j].x = -g[j].x + beta * u[j].x; u[j].y = -g[j].y + beta * u[j].y; }
+                acc[0] = acc[0] + g[j].x * u[j].x;
+                acc[0] = acc[0] + g[j].y * u[j].y;
+            }
+        }
+        cta_allreduce<1>(acc, scratch, phase);
+        return acc[0];
+    }
+    // evalϕdϕ! (cg_utils.jl:3-22) + the dot pack of the trial kernel (same terms, same order)
+    __device__ __forceinline__ void eval_trial(double a, Pack9 &P) {
+        double acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (owns(j)) {
+                double2 p;
+                p.x = x[j].x + a * u[j].x;
+                p.y = x[j].y + a * u[j].y;
+                xp[j] = p;
+                const double t = p.y - p.x * p.x;
+                const double om = 1.0 - p.x;
+                const double f = (100.0 * t) * t + om * om;
+                double2 gn;
+                gn.x = (-400.0 * p.x) * t - 2.0 * om;
+                gn.y = 200.0 * t;
+                gp[j] = gn;
+                const double y1 = gn.x - g[j].x, y2 = gn.y - g[j].y;
+                acc[CGO_P_PHI] = acc[CGO_P_PHI] + f;
+                acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.x * u[j].x;   acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.y * u[j].y;
+                acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.x * gn.x;     acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.y * gn.y;
+                acc[CGO_P_YY] = acc[CGO_P_YY] + y1 * y1;             acc[CGO_P_YY] = acc[CGO_P_YY] + y2 * y2;
+                acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].x * y1;         acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].y * y2;
+                acc[CGO_P_YGP] = acc[CGO_P_YGP] + y1 * gn.x;         acc[CGO_P_YGP] = acc[CGO_P_YGP] + y2 * gn.y;
+                acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.x * g[j].x;     acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.y * g[j].y;
+                acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].x * g[j].x;     acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].y * g[j].y;
+                acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].x * u[j].x;     acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].y * u[j].y;
+            }
+        }
+        cta_allreduce<9>(acc, scratch, phase);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P.v[k] = acc[k];
+        evals++;
+    }
+};
+
+// zoom! (nocedal.jl:162-209)
+template <int NPT>
+__device__ int zoom(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c, double a_lb, double a_ub,
+                    double phi_lb, double phi0, double dphi0, int64_t evals, double &phi_out, double &a_out,
+                    int64_t &evals_out) {
+    double a = 0.0, phi_a = 0.0, dphi_a = 0.0;
+    for (int64_t it = 0; it < c.zoom_max_iters; ++it) {
+        a = (a_lb + a_ub) / 2;                                              // :187
+        S.eval_trial(a, P);                                                 // :190
+        phi_a = P.v[CGO_P_PHI]; dphi_a = P.v[CGO_P_DPHI];
+        evals += 1;
+        if ((phi_a > phi0 + c.c1 * a * dphi0) || (phi_a >= phi_lb)) {       // :193
+            a_ub = a;
+        } else {
+            if (fabs(dphi_a) <= -c.c2 * dphi0) {                            // :196
+                phi_out = phi_a; a_out = a; evals_out = evals;
+                return CGO_ST_SUCCESS;
+            }
+            if (dphi_a * (a_ub - a_lb) >= 0) a_ub = a_lb;                   // :200
+            a_lb = a;
+            phi_lb = phi_a;
+        }
+    }
+    phi_out = phi_a; a_out = a; evals_out = evals;
+    return CGO_ST_ZOOM_MAX_ITERS;                                           // :208
+}
+
+// linesearch! (nocedal.jl:33-158); dphi0 = dot(df_x, u) was reduced by update_dir
+template <int NPT>
+__device__ int linesearch(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0,
+                          double a_initial, double &phi_out, double &a_out, int64_t &evals_out) {
+    if (!(0.0 < a_initial && isfinite(a_initial))) a_initial = 1.0;        // :49-52
+    const double phi0 = f_x;
+    if (dphi0 > 0.0) {                                                      // :57-63
+        phi_out = phi0; a_out = 0.0; evals_out = 0;
+        return CGO_ST_NON_DESCENT;
+    }
+    double a_prev = 0.0, phi_prev = phi0;
+    double a = a_initial, phi_a = phi0, dphi_a = dphi0;
+    double a_max = a * c.growth;
+    int64_t evals = 0;
+    bool non_initial = false;
+    for (int64_t it = 0; it < c.ls_max_iters; ++it) {                       // :76
+        S.eval_trial(a, P);                                                 // :78
+        phi_a = P.v[CGO_P_PHI]; dphi_a = P.v[CGO_P_DPHI];
+        evals += 1;
+        const bool chk1 = phi_a > phi0 + c.c1 * a * dphi0;                  // :81
+        const bool chk2 = phi_a >= phi_prev;                                // :82
+        if (chk1 || (chk2 && non_initial))                                  // :83-105
+            return zoom(S, P, c, a_prev, a, phi_prev, phi0, dphi0, evals, phi_out, a_out, evals_out);
+        if (fabs(dphi_a) <= -c.c2 * dphi0) {                                // :107-110
+            phi_out = phi_a; a_out = a; evals_out = evals;
+            return CGO_ST_SUCCESS;
+        }
+        if (dphi_a >= 0)                                                    // :112-134
+            return zoom(S, P, c, a, a_prev, phi_a, phi0, dphi0, evals, phi_out, a_out, evals_out);
+        a_prev = a; phi_prev = phi_a; non_initial = true;                   // :137-139
+        a_max = a * c.growth;                                               // :143
+        if (a > a_max) {                                                    // :144-149
+            phi_out = phi_a; a_out = a; evals_out = evals;
+            return CGO_ST_A_MAX_OVERFLOW;
+        }
+        a = (a_max + a) / 2;                                                // :150
+    }
+    phi_out = phi_a; a_out = a; evals_out = evals;
+    return CGO_ST_LS_MAX_ITERS;                                             // :157
+}
+
+// getβ from the dot pack (the single-pass forms of conjugategradientoptim.jl_b200/cg_flavours.py)
+__device__ __forceinline__ double get_beta(const cgo_batched_config &c, const Pack9 &P) {
+    const double *v = P.v;
+    switch (c.flavour) {
+    case 1: {                                                               // YuanWangSheng :51-79
+        const double R1 = c.mu * sqrt(v[CGO_P_UU]) * sqrt(v[CGO_P_YY]);     // :65
+        const double R2 = v[CGO_P_UY];                                      // :66
+        const double R3 = 2 * v[CGO_P_YY] * v[CGO_P_DPHI] / v[CGO_P_YGP];   // :67
+        const double R = jl_max(jl_max(R1, R2), R3);                        // :68
+        const double m = 2 * v[CGO_P_YY] / R;                               // :73
+        return (v[CGO_P_YGP] - m * v[CGO_P_DPHI]) / R;
+    }
+    case 2: {                                                               // SallehAlhawarat :133-151
+        const double nrm = sqrt(v[CGO_P_GPGP]);
+        const double norm_sq = nrm * nrm;                                   // :140
+        const double tmp = v[CGO_P_GPG];                                    // :141
+        if (norm_sq > tmp) return (norm_sq - tmp) / (v[CGO_P_DPHI] - v[CGO_P_UG]);   // :145
+        return 0.0;
+    }
+    case 3:                                                                 // LiuStorrey :157-170
+        return v[CGO_P_YGP] / (-v[CGO_P_UY]);
+    default: {                                                              // HagerZhang :87-108
+        const double R = v[CGO_P_UY];                                       // :98
+        const double m = 2 * v[CGO_P_YY] / R;                               // :102
+        return (v[CGO_P_YGP] - m * v[CGO_P_DPHI]) / R;
+    }
+    }
+}
+
+struct BatchedOut {
+    double *objective, *minimizer, *grad_norm;
+    int64_t *iters_ran, *fdf_evals;
+    int32_t *status;
+};
+
+template <int NPT>
+__global__ void __launch_bounds__(BT, NPT <= 2 ? 2 : 1)
+k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_batched_config c, BatchedOut out) {
+    __shared__ double scratch[2 * 9 * NW];
+    for (int64_t prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+        Problem<NPT> S;
+        S.n = n; S.scratch = scratch; S.phase = 0; S.evals = 0;
+        const double2 *xin = reinterpret_cast<const double2 *>(x0 + prob * (int64_t)n);
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (S.owns(j)) S.x[j] = xin[threadIdx.x + j * BT];              // optim.jl:21 x = copy(x_initial)
+        }
+        double f_x, gg;
+        S.eval_initial(f_x, gg);                                            // :25
+        double norm_g = sqrt(gg);                                           // :26
+        const double f_x0 = f_x;                                            // :31
+        double dphi0 = S.update_dir(0.0, true);                             // :46  u = −g
+        double a_initial = nan("");                                         // :47
+        int status = CGO_ST_MAX_ITERS_REACHED;
+        int64_t iters_ran = c.max_iters;
+        Pack9 P;
+        for (int64_t it = 1; it <= c.max_iters; ++it) {                     // :50
+            if (isfinite(f_x) && isfinite(norm_g) && norm_g < c.eps) {      // :53-80
+                status = (f_x <= f_x0) ? CGO_ST_SUCCESS : CGO_ST_INCREASING_OBJECTIVE;
+                iters_ran = it - 1;
+                break;
+            }
+            double f_xp, a_star;
+            int64_t evals;
+            const int st = linesearch(S, P, c, f_x, dphi0, a_initial, f_xp, a_star, evals);   // :83
+            a_initial = a_star;                                             // :92
+            if (st != CGO_ST_SUCCESS) { status = st; iters_ran = it - 1; break; }            // :93-104
+            const double norm_gp = sqrt(P.v[CGO_P_GPGP]);                   // :107
+            if (!isfinite(f_xp) || !isfinite(norm_gp)) {                    // :108-121
+                status = CGO_ST_NON_FINITE_PROPOSED; iters_ran = it - 1; break;
+            }
+            const double beta = get_beta(c, P);                             // :130-135
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) { S.x[j] = S.xp[j]; S.g[j] = S.gp[j]; }             // :136-140
+            f_x = f_xp; norm_g = norm_gp;                                   // :138, :141
+            dphi0 = S.update_dir(beta, false);                              // :145
+        }
+        // Results (types.jl:107-151)
+        double2 *xout = out.minimizer ? reinterpret_cast<double2 *>(out.minimizer + prob * (int64_t)n) : nullptr;
+        if (xout) {
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                if (S.owns(j)) xout[threadIdx.x + j * BT] = S.x[j];
+            }
+        }
+        if (threadIdx.x == 0) {
+            if (out.objective) out.objective[prob] = f_x;
+            if (out.grad_norm) out.grad_norm[prob] = norm_g;
+            if (out.iters_ran) out.iters_ran[prob] = iters_ran;
+            if (out.status) out.status[prob] = status;
+            if (out.fdf_evals) out.fdf_evals[prob] = S.evals;
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+int dev_alloc(T **p, size_t count) {
+    CGO_CUDA(cudaMalloc(p, sizeof(T) * (count > 0 ? count : 1)));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int32_t n, const double *x0,
+                                               const cgo_batched_config *cfg, double *objective,
+                                               int64_t *iters_ran, int32_t *status, int64_t *fdf_evals,
+                                               double *minimizer, double *grad_norm) {
+    CGO_CHECK(ctx && x0 && cfg, "NULL argument");
+    CGO_CHECK(nprob >= 0, "nprob < 0");
+    CGO_CHECK(n >= 2 && n % 2 == 0 && n <= 2 * BT * CGO_U_VEC, "n must be even and in [2, %d]", 2 * BT * CGO_U_VEC);
+    CGO_CHECK(0.0 < cfg->eps && cfg->eps < 1.0, "need 0 < eps < 1 (types.jl:187)");
+    CGO_CHECK(0.0 < cfg->c1 && cfg->c1 < cfg->c2 && cfg->c2 < 1.0 && cfg->growth > 1.0 && cfg->ls_max_iters >= 0 &&
+                  cfg->zoom_max_iters >= 0, "StrongWolfeBisection config asserts failed (nocedal.jl:22-26)");
+    CGO_CHECK(cfg->flavour >= 0 && cfg->flavour <= 3, "flavour %d out of [0,3]", cfg->flavour);
+    if (nprob == 0) return 0;
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t nx = (size_t)nprob * (size_t)n;
+    double *d_x0 = nullptr;
+    BatchedOut o{};
+    int rc = 0;
+    auto body = [&]() -> int {
+        CGO_TRY(dev_alloc(&d_x0, nx));
+        CGO_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * nx, cudaMemcpyHostToDevice, s));
+        if (objective) CGO_TRY(dev_alloc(&o.objective, (size_t)nprob));
+        if (grad_norm) CGO_TRY(dev_alloc(&o.grad_norm, (size_t)nprob));
+        if (iters_ran) CGO_TRY(dev_alloc(&o.iters_ran, (size_t)nprob));
+        if (fdf_evals) CGO_TRY(dev_alloc(&o.fdf_evals, (size_t)nprob));
+        if (status) CGO_TRY(dev_alloc(&o.status, (size_t)nprob));
+        if (minimizer) CGO_TRY(dev_alloc(&o.minimizer, nx));
+        const int npt = (n + 2 * BT - 1) / (2 * BT);                        // double2 items per lane
+        const int occ = npt <= 2 ? 2 : 1;
+        int64_t cap = (int64_t)ctx->sms * occ * 4;                          // a few waves of persistent CTAs
+        const int grid = (int)(nprob < cap ? nprob : cap);
+        cgo_timer_begin(ctx, CGO_T_BATCHED);
+        if (npt <= 1) k_batched_rosenbrock<1><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
+        else if (npt <= 2) k_batched_rosenbrock<2><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
+        else k_batched_rosenbrock<4><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
+        cgo_timer_end(ctx);
+        ctx->launches++;
+        CGO_CUDA(cudaGetLastError());
+        if (objective) CGO_CUDA(cudaMemcpyAsync(objective, o.objective, sizeof(double) * nprob, cudaMemcpyDeviceToHost, s));
+        if (grad_norm) CGO_CUDA(cudaMemcpyAsync(grad_norm, o.grad_norm, sizeof(double) * nprob, cudaMemcpyDeviceToHost, s));
+        if (iters_ran) CGO_CUDA(cudaMemcpyAsync(iters_ran, o.iters_ran, sizeof(int64_t) * nprob, cudaMemcpyDeviceToHost, s));
+        if (fdf_evals) CGO_CUDA(cudaMemcpyAsync(fdf_evals, o.fdf_evals, sizeof(int64_t) * nprob, cudaMemcpyDeviceToHost, s));
+        if (status) CGO_CUDA(cudaMemcpyAsync(status, o.status, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s));
+        if (minimizer) CGO_CUDA(cudaMemcpyAsync(minimizer, o.minimizer, sizeof(double) * nx, cudaMemcpyDeviceToHost, s));
+        CGO_CUDA(cudaStreamSynchronize(s));
+        if (ctx->timing) cgo_timer_collect(ctx);
+        return 0;
+    };
+    rc = body();
+    cudaFree(d_x0); cudaFree(o.objective); cudaFree(o.grad_norm); cudaFree(o.iters_ran);
+    cudaFree(o.fdf_evals); cudaFree(o.status); cudaFree(o.minimizer);
+    return rc;
+}

@@ -392,3 +392,59 @@ class DeviceLineSearchContainer:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------- batched
+STATUS_SYMBOLS = (
+    "incomplete", "success", "increasing_objective", "max_iters_reached",
+    "non_finite_objective_or_gradient_proposed", "non_descent_search_direction",
+    "linesearch_a_max_overflow", "linesearch_max_iters_reached", "zoom_max_iters_reached",
+    "accepted_non_finite_iterate", "cannot_find_initial_feasible_step", "max_step_length_reached",
+    "cannot_find_feasible_step", "non_finite_step_proposed", "proposed_step_same_as_current_step",
+    "step_bracket_precision_issue")
+
+
+class BatchedResults:
+    """Per-problem Results fields (types.jl:107-114) of a batched run, as arrays."""
+
+    def __init__(self, objective, minimizer, grad_norm, iters_ran, status_code, fdf_evals):
+        self.objective, self.minimizer, self.grad_norm = objective, minimizer, grad_norm
+        self.iters_ran, self.status_code, self.fdf_evals = iters_ran, status_code, fdf_evals
+
+    @property
+    def status(self):
+        return [STATUS_SYMBOLS[c] for c in self.status_code]
+
+
+def minimizeobjective_batched(x_initial, config, linesearch_config, ctx: Optional[Context] = None,
+                              want_minimizer: bool = True) -> BatchedResults:
+    """`minimizeobjective` (src/engine/optim.jl:6-171) for MANY independent extended-Rosenbrock
+    problems at once (BASELINE.json configs[4]): `x_initial` is (nprob, n), one CTA solves one
+    problem entirely on the device (StrongWolfeBisection line search, any of the four CG
+    flavours), no communication between problems."""
+    from .cg_flavours import HagerZhang, LiuStorrey, SallehAlhawarat, YuanWangSheng
+    from .linesearch.nocedal import StrongWolfeBisection
+    ctx = ctx or default_context()
+    X0 = np.ascontiguousarray(x_initial, dtype=np.float64)
+    if X0.ndim != 2:
+        raise ValueError("x_initial must be (nprob, n)")
+    nprob, n = X0.shape
+    if not isinstance(linesearch_config, StrongWolfeBisection):
+        raise TypeError("the batched solver implements StrongWolfeBisection (SURVEY.md §8f N2 lists the others as next)")
+    β = config.β_config
+    flav = {HagerZhang: 0, YuanWangSheng: 1, SallehAlhawarat: 2, LiuStorrey: 3}.get(type(β))
+    if flav is None:
+        raise TypeError(f"the batched solver has no {type(β).__name__} flavour")
+    bc = capi.BatchedConfig(eps=config.ϵ, max_iters=config.max_iters, flavour=flav, _pad=0,
+                            mu=getattr(β, "μ", 0.0), c1=linesearch_config.c1, c2=linesearch_config.c2,
+                            growth=linesearch_config.a_max_growth_factor,
+                            ls_max_iters=linesearch_config.max_iters,
+                            zoom_max_iters=linesearch_config.zoom_max_iters)
+    obj, gn = np.empty(nprob), np.empty(nprob)
+    it, ev = np.empty(nprob, dtype=np.int64), np.empty(nprob, dtype=np.int64)
+    st = np.empty(nprob, dtype=np.int32)
+    xm = np.empty((nprob, n)) if want_minimizer else None
+    check(lib().cgo_batched_minimize_rosenbrock(
+        ctx.h, nprob, n, dptr(X0.reshape(-1)), C.byref(bc), dptr(obj), it.ctypes.data, st.ctypes.data,
+        ev.ctypes.data, dptr(xm.reshape(-1)) if want_minimizer else None, dptr(gn)))
+    return BatchedResults(obj, xm, gn, it, st, ev)
