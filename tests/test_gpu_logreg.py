@@ -1,0 +1,100 @@
+"""GPU parity tests of the CSR logistic-regression objective (BASELINE.json configs[3], L-BFGS).
+The generator, CSR, transpose and all IEEE arithmetic are bit-exact against the oracle; the loss
+uses exp / log1p, whose CUDA and glibc implementations may differ in the last ulp, so f and g are
+compared at 1e-13 relative and whole L-BFGS traces at north_star's 1e-10."""
+import numpy as np
+import pytest
+
+import cgoptim_b200 as cg
+from oracle import oracle as O
+
+from helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("N,d,K", [(3000, 500, 20), (10_000, 4000, 7), (257, 64, 4)])
+def test_generator_labels_transpose_bit_exact(ctx, N, d, K):
+    obj = cg.LogRegGPU(N, d, K, 24, 1e-4, ctx)
+    ora = O.Objective.logreg(N, d, K, 24, 1e-4)
+    rp, ci, va, y = obj.csr(False)
+    orp, oci, ova = ora.csr(False)
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+    assert np.array_equal(y, ora.rhs()) and set(np.unique(y)) <= {-1.0, 1.0}
+    rpT, ciT, vaT, _ = obj.csr(True)
+    orpT, ociT, ovaT = ora.csr(True)
+    assert np.array_equal(rpT, orpT) and np.array_equal(ciT, ociT) and np.array_equal(vaT, ovaT)
+    x = np.random.default_rng(0).standard_normal(d)
+    assert np.array_equal(obj.spmv(x), ora.spmv(x))                 # margins: IEEE only, bit-exact
+    obj.close()
+
+
+@pytest.mark.parametrize("N,d,K", [(3000, 500, 20), (20_000, 3000, 20)])
+def test_f_and_g_match_oracle(ctx, N, d, K):
+    lam = 1e-4
+    obj = cg.LogRegGPU(N, d, K, 24, lam, ctx)
+    ora = O.Objective.logreg(N, d, K, 24, lam)
+    ora.set_sum_mode("cgo")
+    rng = np.random.default_rng(1)
+    for scale in (0.0, 0.1, 3.0, 40.0):                             # incl. saturated sigmoids
+        w = scale * rng.standard_normal(d)
+        ws = obj.make_workspace(w, fuse_direction=False)
+        f, g = ora.fdf(w)
+        assert abs(ws.f_x0 - f) <= 1e-13 * max(abs(f), 1e-300)
+        gd = ws.download()[1]
+        assert np.max(np.abs(gd - g)) <= 1e-13 * np.max(np.abs(g))
+        ws.close()
+    obj.close()
+
+
+def test_gradient_matches_finite_differences(ctx):
+    N, d = 2000, 60
+    obj = cg.LogRegGPU(N, d, 6, 5, 1e-3, ctx)
+    w = 0.3 * np.random.default_rng(2).standard_normal(d)
+    ws = obj.make_workspace(w, fuse_direction=False)
+    g = ws.download()[1]
+    ws.close()
+    h = 1e-5
+    for i in (0, 7, 59):
+        e = np.zeros(d); e[i] = h
+        a = obj.make_workspace(w + e, fuse_direction=False); fp = a.f_x0; a.close()
+        b = obj.make_workspace(w - e, fuse_direction=False); fm = b.f_x0; b.close()
+        assert abs((fp - fm) / (2 * h) - g[i]) <= 1e-7 * max(1.0, abs(g[i]))
+    obj.close()
+
+
+@pytest.mark.parametrize("flavour", ["LBFGS", "HagerZhang"])
+def test_lbfgs_run_matches_oracle(ctx, flavour):
+    """cfg 4 shape at test size: L-BFGS m = 10, StrongWolfe(c1 = 1e-4, c2 = 0.9), w0 = 0."""
+    N, d, lam = 20_000, 2000, 1e-4
+    ocfg, cfg, ls = make_pair(flavour, "StrongWolfeBisection", eps=1e-6, max_iters=60, c1=1e-4, c2=0.9, lbfgs_m=10)
+    obj = cg.LogRegGPU(N, d, 20, 24, lam, ctx)
+    ora = O.minimize(O.Objective.logreg(N, d, 20, 24, lam), np.zeros(d), ocfg)
+    ret = cg.minimizeobjective(obj, np.zeros(d), cfg, ls)
+    k = min(50, len(ora.trace_objective), len(ret.trace.objective))
+    assert k >= 10
+    assert np.array_equal(ret.trace.step_size[:k], ora.trace_step_size[:k])          # identical decisions
+    assert np.array_equal(ret.trace.objective_evals[:k], ora.trace_objective_evals[:k])
+    np.testing.assert_allclose(ret.trace.objective[:k], ora.trace_objective[:k], rtol=1e-10)
+    np.testing.assert_allclose(ret.trace.grad_norm[:k], ora.trace_grad_norm[:k], rtol=1e-8)
+    assert ret.status == ora.status and abs(ret.iters_ran - ora.iters_ran) <= 2
+    assert abs(ret.objective - ora.objective) <= 1e-8 * abs(ora.objective)
+    assert ret.trace.objective[k - 1] < 0.9 * ret.trace.objective[0]
+    obj.close()
+
+
+def test_run_to_run_reproducible(ctx):
+    N, d = 50_000, 5000
+    _, cfg, ls = make_pair("LBFGS", max_iters=15, c1=1e-4, c2=0.9)
+    obj = cg.LogRegGPU(N, d, 20, 24, 1e-6, ctx)
+    a = cg.minimizeobjective(obj, np.zeros(d), cfg, ls)
+    b = cg.minimizeobjective(obj, np.zeros(d), cfg, ls)
+    assert np.array_equal(a.trace.objective, b.trace.objective) and np.array_equal(a.minimizer, b.minimizer)
+    obj.close()
