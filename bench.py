@@ -30,8 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FULL_N = {"sparse_ls": 200_000_000, "rosenbrock": 100_000_000}
-SAMPLE_N = {"sparse_ls": 4_000_000, "rosenbrock": 20_000_000}   # CPU-arm sample sizes
+FULL_N = {"sparse_ls": 200_000_000, "rosenbrock": 100_000_000, "logreg": 20_000_000, "batched": 512}
+SAMPLE_N = {"sparse_ls": 4_000_000, "rosenbrock": 20_000_000, "logreg": 400_000, "batched": 512}   # CPU-arm sample sizes
+LOGREG_SAMPLES_PER_FEATURE = 2.5      # cfg 4: 5e7 samples x 2e7 features, 20 nnz/row
+BATCHED_NPROB = 262_144               # cfg 5
 
 
 def parse():
@@ -40,7 +42,7 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="sparse_ls", choices=["sparse_ls", "rosenbrock"])
+    p.add_argument("--workload", default="sparse_ls", choices=["sparse_ls", "rosenbrock", "logreg", "batched"])
     p.add_argument("--n", type=int, default=0, help="problem size (default: BASELINE.json's)")
     p.add_argument("--coh", type=int, default=30,
                    help="sparse_ls generator: log2 of the number of consecutive rows sharing their column "
@@ -73,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -113,9 +115,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ workloads
-def solver_configs(cg, max_iters):
+def solver_configs(cg, max_iters, workload="sparse_ls"):
     # examples/min.jl:16-35: HagerZhang, StrongWolfeBisection(c1=1e-5, c2=0.8, growth 2, 1000, 100).
     # ϵ is set far below reach so that W+K iterations always run (the metric is iterations/s).
+    if workload == "logreg":          # SURVEY.md §8d cfg 4: LBFGS(m=10) + StrongWolfe(1e-4, 0.9)
+        cfg = cg.setupCGConfig(1e-300, cg.LBFGS(10), cg.EnableTrace(), max_iters=max_iters)
+        ls = cg.setupStrongWolfeBisection(1e-4, 0.9, a_max_growth_factor=2.0, max_iters=1000, zoom_max_iters=100)
+        return cfg, ls
     cfg = cg.setupCGConfig(1e-300, cg.HagerZhang(), cg.EnableTrace(), max_iters=max_iters)
     ls = cg.setupStrongWolfeBisection(1e-5, 0.8, a_max_growth_factor=2.0, max_iters=1000, zoom_max_iters=100)
     return cfg, ls
@@ -125,6 +131,9 @@ def make_objective(cg, args, ctx, n):
     if args.workload == "rosenbrock":
         obj = cg.RosenbrockGPU(n, ctx)
         x0 = obj.default_x0(24, 0.1)
+    elif args.workload == "logreg":
+        obj = cg.LogRegGPU(int(n * LOGREG_SAMPLES_PER_FEATURE), n, 20, 24, 1e-6, ctx)
+        x0 = np.zeros(obj.n_local)
     else:
         obj = cg.SparseLSGPU(n, 10, None, 24, args.coh, ctx)
         x0 = np.zeros(obj.n_local)
@@ -146,6 +155,13 @@ def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
     pass and the direction pass it counts separately are fused away here.)"""
     if args.workload == "rosenbrock":
         return 8.0 * n_local * (6 * iters + 5 * (evals - iters))
+    if args.workload == "logreg":
+        # K_a 24d | K_b A + gather w 8d + R y 8N + W c 8N | K_c Aᵀ + gather c 8N + R u,g,w 24d + W g⁺ 8d;
+        # per iteration: K_a of the first trial is unfused (24d), pair staging R 4 vectors W 2 = 48d,
+        # two-loop recursion with m = 10: 8d(4m + 3) (DESIGN.md)
+        d, N = n_local, int(n_local * LOGREG_SAMPLES_PER_FEATURE)
+        per_eval = (12.0 * nnz_local + 8.0 * (N + 1)) + (12.0 * nnz_local + 8.0 * (d + 1)) + 64.0 * d + 24.0 * N
+        return evals * per_eval + iters * (48.0 * d + 8.0 * d * 43)
     per_eval = 2 * matrix_bytes(n_local, nnz_local) + 80.0 * n_local
     return evals * per_eval + 16.0 * n_local * iters
 
@@ -174,7 +190,9 @@ def run_ours(args):
     obj, x0 = make_objective(cg, args, ctx, n)
     n_local = obj.n_local
     nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
-    cfg, ls = solver_configs(cg, W + K + 1)
+    if args.workload == "logreg":
+        nnz_local = 20 * int(n * LOGREG_SAMPLES_PER_FEATURE)
+    cfg, ls = solver_configs(cg, W + K + 1, args.workload)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -222,6 +240,13 @@ def run_ours(args):
         dom = "trial"
         dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
         dom_ms, dom_cnt = timers["trial"]
+    elif args.workload == "logreg":
+        dom = "k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack)"
+        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
+        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
+        d, N = n_local, int(n_local * LOGREG_SAMPLES_PER_FEATURE)
+        dom_bytes = (dom_cnt / 2.0) * ((12.0 * nnz_local + 8.0 * (N + 1)) + (12.0 * nnz_local + 8.0 * (d + 1))
+                                        + 40.0 * d + 24.0 * N)
     else:
         dom = "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)"
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]
@@ -241,11 +266,11 @@ def run_ours(args):
     # ---------------- end-to-end through the public API (`e2e`) ----------------
     e2e = None
     if not args.no_e2e:
-        cfg2, ls2 = solver_configs(cg, K)
+        cfg2, ls2 = solver_configs(cg, K, args.workload)
         x0p = torch.from_numpy(x0.copy()).pin_memory().numpy()
         # one untimed call first: page-locks the result buffers (they are pooled and reused) and
         # warms the allocator, as a long-running host would have done
-        cfg1, ls1 = solver_configs(cg, 1)
+        cfg1, ls1 = solver_configs(cg, 1, args.workload)
         cg.minimizeobjective(obj, x0p, cfg1, ls1)
         barrier()
         t0 = time.perf_counter()
@@ -268,7 +293,8 @@ def run_ours(args):
     line = None
     if rank == 0:
         line = {
-            "metric": "cg_iterations_per_s", "value": round(K / (ms * 1e-3), 4), "unit": "iterations/s",
+            "metric": "lbfgs_iterations_per_s" if args.workload == "logreg" else "cg_iterations_per_s",
+            "value": round(K / (ms * 1e-3), 4), "unit": "iterations/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -277,6 +303,9 @@ def run_ours(args):
                                     + ("ten diagonals" if args.coh >= 28 else "offsets redrawn every 2^%d rows" % args.coh)
                                     + "), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
                                     if args.workload == "sparse_ls" else
+                                    f"CSR logistic regression {int(n * LOGREG_SAMPLES_PER_FEATURE)} samples x {n} features, "
+                                    f"20 nnz/row, lambda 1e-6, L-BFGS m=10 + StrongWolfeBisection(1e-4,0.9)"
+                                    if args.workload == "logreg" else
                                     f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
                        "n": n, "sharding": f"rows/vector slices over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (vectors are 8n bytes >> 126 MB)",
@@ -285,6 +314,75 @@ def run_ours(args):
             "host_wall_ms_per_step": round(wall_ms / K, 4),
             "objective_trace_head": [float(v) for v in trace_f[:4]],
         }
+    return line, ctx
+
+
+# ------------------------------------------------------------------------------ batched (cfg 5)
+def run_batched(args):
+    """BASELINE.json configs[4]: 262,144 independent n = 512 Rosenbrock problems, HZ + strong Wolfe,
+    one CTA per problem, problems split over the ranks without communication ("weak" per problem;
+    total work fixed).  A step = one whole batched solve of this rank's share."""
+    import torch
+    import cgoptim_b200 as cg
+    from oracle import oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = cg.Context(local_rank)
+    n = args.n or 512
+    nprob = BATCHED_NPROB // world
+    rng = np.random.default_rng(24 + rank)
+    X0 = np.tile([-1.2, 1.0], n // 2)[None, :] + 0.1 * (2.0 * rng.random((nprob, n)) - 1.0)
+    X0p = torch.from_numpy(X0).pin_memory().numpy()
+    cfg = cg.setupCGConfig(1e-5, cg.HagerZhang(), cg.DisableTrace(), max_iters=1000)
+    ls = cg.setupStrongWolfeBisection(1e-5, 0.8, a_max_growth_factor=2.0, max_iters=1000, zoom_max_iters=100)
+    K, W = max(args.steps // 10, 2), max(min(args.warmup, 3), 1)
+    for _ in range(W):
+        res = cg.minimizeobjective_batched(X0p, cfg, ls, ctx)
+    ctx.timing(True)
+    ctx.timing_read(reset=True)
+    l0 = ctx.kernel_launches
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        res = cg.minimizeobjective_batched(X0p, cfg, ls, ctx)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kms = ctx.timing_read(reset=True)["batched"][0]
+    ctx.timing(False)
+    t = torch.tensor([kms, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kms, wall = float(t[0].item()), float(t[1].item())
+    iters = torch.tensor([float(res.iters_ran.sum()), float(res.fdf_evals.sum()),
+                          float((res.status_code == 1).sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(iters)
+    tot_it, tot_ev, tot_ok = (float(v) for v in iters.tolist())
+    line = None
+    if rank == 0:
+        line = {"metric": "batched_cg_iterations_per_s", "value": round(tot_it * K / (kms * 1e-3), 1),
+                "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(kms / K, 3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{BATCHED_NPROB} independent extended-Rosenbrock problems n={n}, Hager-Zhang CG + "
+                                       f"StrongWolfeBisection(1e-5,0.8), eps 1e-5, one CTA per problem, whole solver on device",
+                           "problems_per_s": round(nprob * world * K / (kms * 1e-3), 1),
+                           "iterations_total": tot_it, "fdf_evals_total": tot_ev, "converged": tot_ok,
+                           "l2_policy": "on-chip workload: x0 read once, result written once (HBM roofline not applicable)"},
+                "roofline": {"bound": "on-chip latency (registers + shuffles); HBM roofline not applicable", "achieved": None,
+                             "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                             "fp64_gflops_estimate": round(tot_ev * K * (n / 2) * 49 / (kms * 1e-3) / 1e9, 1)},
+                "e2e": {"value": round(tot_it * K / wall, 1), "unit": "iterations/s",
+                        "h2d_bytes_per_step": 8.0 * nprob * n, "d2h_bytes_per_step": 8.0 * nprob * n + 36.0 * nprob,
+                        "includes": "x0 H2D from pinned memory, solve, minimizers + per-problem results D2H"},
+                "gpu_launches": int(ctx.kernel_launches - l0), "clocks": None, "cpu_baseline": None}
     return line, ctx
 
 
@@ -297,11 +395,18 @@ def run_cpu(args, steps, warmup, threads):
     if args.workload == "rosenbrock":
         obj = O.Objective.rosenbrock(n)
         x0 = O.rosenbrock_x0(n, 24, 0.1)
+    elif args.workload == "logreg":
+        obj = O.Objective.logreg(int(n * LOGREG_SAMPLES_PER_FEATURE), n, 20, 24, 1e-6, threads)
+        x0 = np.zeros(n)
     else:
         obj = O.Objective.sparse_ls(n, 10, min(1 << 20, (n - 1) // 2), 24, args.coh, threads)
         x0 = np.zeros(n)
-    mk = lambda it: O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-300, max_iters=it,
-                                  sum_mode="seq", beta_form="literal", threads=threads)
+    if args.workload == "logreg":
+        mk = lambda it: O.make_config("LBFGS", "StrongWolfeBisection", eps=1e-300, max_iters=it, lbfgs_m=10,
+                                      c1=1e-4, c2=0.9, sum_mode="seq", threads=threads)
+    else:
+        mk = lambda it: O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-300, max_iters=it,
+                                      sum_mode="seq", beta_form="literal", threads=threads)
     if warmup:
         O.minimize(obj, x0, mk(warmup), trace=False)
     t0 = time.perf_counter()
@@ -336,10 +441,10 @@ def main():
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    line, ctx = run_ours(args)
+    line, ctx = run_batched(args) if args.workload == "batched" else run_ours(args)
     if rank == 0:
         world = int(os.environ.get("WORLD_SIZE", "1"))
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload != "batched":
             line["cpu_baseline"] = run_cpu(args, 5, 0, os.cpu_count() or 1)
         else:
             line["cpu_baseline"] = None

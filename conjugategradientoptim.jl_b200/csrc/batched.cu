@@ -27,11 +27,14 @@ constexpr int NW = CGO_NW;
 
 struct Pack9 { double v[9]; };
 
-// canonical CTA combine, result broadcast to every lane (double-buffered scratch: one barrier)
+// canonical CTA combine, result broadcast to every lane.  The warp-ordered final sums are done by
+// K lanes of warp 0 only (FP64 issue slots are the scarce resource of this kernel: having all 256
+// lanes repeat the 8-term sums costs 40 % more FP64 instructions than the objective itself).
 template <int K>
-__device__ __forceinline__ void cta_allreduce(double (&acc)[K], double *scratch /* 2 * K * NW */, int &phase) {
+__device__ __forceinline__ void cta_allreduce(double (&acc)[K], double *scratch /* K * NW + 2 * K */, int &phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sm = scratch + phase * (K * NW);
+    double *sm = scratch;
+    double *res = scratch + 9 * NW + phase * 9;      // double-buffered results: no third barrier
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double v = acc[k];
@@ -40,13 +43,16 @@ __device__ __forceinline__ void cta_allreduce(double (&acc)[K], double *scratch 
         if (lane == 0) sm[k * NW + warp] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
+    if (threadIdx.x < K) {
+        const int k = threadIdx.x;
         double s = sm[k * NW];
 #pragma unroll
         for (int w = 1; w < NW; ++w) s = s + sm[k * NW + w];
-        acc[k] = s;
+        res[k] = s;
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = res[k];
     phase ^= 1;
 }
 
@@ -242,9 +248,9 @@ struct BatchedOut {
 };
 
 template <int NPT>
-__global__ void __launch_bounds__(BT, NPT <= 2 ? 2 : 1)
+__global__ void __launch_bounds__(BT, NPT == 1 ? 3 : (NPT == 2 ? 2 : 1))
 k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_batched_config c, BatchedOut out) {
-    __shared__ double scratch[2 * 9 * NW];
+    __shared__ double scratch[9 * NW + 2 * 9];
     for (int64_t prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
         Problem<NPT> S;
         S.n = n; S.scratch = scratch; S.phase = 0; S.evals = 0;
@@ -338,7 +344,7 @@ extern "C" int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int3
         if (status) CGO_TRY(dev_alloc(&o.status, (size_t)nprob));
         if (minimizer) CGO_TRY(dev_alloc(&o.minimizer, nx));
         const int npt = (n + 2 * BT - 1) / (2 * BT);                        // double2 items per lane
-        const int occ = npt <= 2 ? 2 : 1;
+        const int occ = npt <= 1 ? 3 : (npt <= 2 ? 2 : 1);
         int64_t cap = (int64_t)ctx->sms * occ * 4;                          // a few waves of persistent CTAs
         const int grid = (int)(nprob < cap ? nprob : cap);
         cgo_timer_begin(ctx, CGO_T_BATCHED);
