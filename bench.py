@@ -140,6 +140,14 @@ def make_objective(cg, args, ctx, n):
     return obj, x0
 
 
+def shard_len(n, world, rank, align=2):
+    """length of cgo_shard_range(n, world, rank, align)"""
+    units = n // align
+    lo = (units * rank // world) * align
+    hi = n if rank == world - 1 else (units * (rank + 1) // world) * align
+    return hi - lo
+
+
 def matrix_bytes(n_local, nnz_local):
     """one streaming pass over a CSR matrix: 8 B value + 4 B column index per entry + row pointers"""
     return 12.0 * nnz_local + 8.0 * (n_local + 1)
@@ -156,14 +164,28 @@ def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
     if args.workload == "rosenbrock":
         return 8.0 * n_local * (6 * iters + 5 * (evals - iters))
     if args.workload == "logreg":
-        # K_a 24d | K_b A + gather w 8d + R y 8N + W c 8N | K_c Aᵀ + gather c 8N + R u,g,w 24d + W g⁺ 8d;
         # per iteration: K_a of the first trial is unfused (24d), pair staging R 4 vectors W 2 = 48d,
         # two-loop recursion with m = 10: 8d(4m + 3)
-        d, N = n_local, int(n_local * LOGREG_SAMPLES_PER_FEATURE)
-        per_eval = (12.0 * nnz_local + 8.0 * (N + 1)) + (12.0 * nnz_local + 8.0 * (d + 1)) + 64.0 * d + 24.0 * N
-        return evals * per_eval + iters * (48.0 * d + 8.0 * d * 43)
+        per_eval, _ = logreg_bytes(args, n_local, nnz_local)
+        return evals * per_eval + iters * (48.0 * n_local + 8.0 * n_local * 43)
     per_eval = 2 * matrix_bytes(n_local, nnz_local) + 80.0 * n_local
     return evals * per_eval + 16.0 * n_local * iters
+
+
+def logreg_bytes(args, d_loc, nnz_loc):
+    """(algorithmic bytes of one fdf! on this rank, of which the K_b + K_c launch pair)
+    one rank:  K_a 24d | K_b A + gather w 8d + R y 8N + W c 8N | K_c Aᵀ + gather c 8N + R u,g,w 24d + W g⁺ 8d
+    R ranks:   K_a 24d_loc | K_b A_r + gather w 8d + R y, W c 16N_loc | K_c Aᵀ_r + gather c 8N_loc + W part 8d |
+               combine R (R parts + u,g,w) W g⁺ = 8d_loc(R + 4)   (exchanges travel over NVLink, not HBM-counted)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    d = args.n or FULL_N["logreg"]
+    N_loc = nnz_loc // 20
+    mats = (12.0 * nnz_loc + 8.0 * (N_loc + 1)) + (12.0 * nnz_loc + 8.0 * (d + 1))
+    if world == 1:
+        pair = mats + 40.0 * d + 24.0 * N_loc
+        return pair + 24.0 * d, pair
+    pair = mats + 16.0 * d + 24.0 * N_loc
+    return pair + 24.0 * d_loc + 8.0 * d_loc * (world + 4), pair
 
 
 def run_ours(args):
@@ -191,7 +213,7 @@ def run_ours(args):
     n_local = obj.n_local
     nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
     if args.workload == "logreg":
-        nnz_local = 20 * int(n * LOGREG_SAMPLES_PER_FEATURE)
+        nnz_local = 20 * shard_len(int(n * LOGREG_SAMPLES_PER_FEATURE), world, rank)
     cfg, ls = solver_configs(cg, W + K + 1, args.workload)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
@@ -202,6 +224,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`) ----------------
+    # The metric is iterations/s with ϵ out of reach, so a run only ends when the line search hits
+    # the FP64 floor of the objective (≈53 iterations on cfg 3, ≈28 on cfg 4: both problems are
+    # well conditioned).  When that happens inside the timed region, the clock stops at the end of
+    # the last completed iteration (the 100-trial zoom that fails is not an iteration and is not
+    # timed) and a fresh run is started from x0 (state allocation and the f/g evaluation at x0 are
+    # set-up, as for the first run).  With the default K + W <= 50 this never triggers on cfg 3.
     run = cg.MinimizerRun(obj, x0, cfg, ls)
     for _ in range(W):
         assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
@@ -211,17 +239,40 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ctx.kernel_launches
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(K):
-        assert run.step() is None, f"run ended inside the timed region: {run.ret.status}"
-    e1.record(stream)
+    launches = 0
+    ms, wall_ms, evals, done, restarts, life = 0.0, 0.0, 0, 0, 0, None
+    trace_f = None
+    while done < K:
+        e0 = torch.cuda.Event(enable_timing=True)
+        t0 = t1 = time.perf_counter()
+        e0.record(stream)
+        e1 = e0
+        ended = False
+        l0 = l1 = ctx.kernel_launches
+        while done < K:
+            if run.step() is not None:      # line search at the FP64 floor: that step is not timed
+                ended = True
+                break
+            done += 1
+            evals += int(run.fdf_evals_ran)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(stream)
+            t1 = time.perf_counter()
+            l1 = ctx.kernel_launches
+        torch.cuda.synchronize()
+        launches += l1 - l0
+        wall_ms += (t1 - t0) * 1e3
+        if e1 is not e0:
+            ms += e0.elapsed_time(e1)
+        if trace_f is None:
+            trace_f = run.ret.trace.objective[:max(run.n - 1, 0)].copy()
+        if ended and done < K:
+            assert run.ret.iters_ran > 0, f"restarted run made no progress: {run.ret.status}"
+            life = run.ret.iters_ran if life is None else min(life, run.ret.iters_ran)
+            run.info.close()
+            run = cg.MinimizerRun(obj, x0, cfg, ls)
+            restarts += 1
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms = e0.elapsed_time(e1)
-    launches = ctx.kernel_launches - l0
     timers = ctx.timing_read(reset=True)
     ctx.timing(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -230,23 +281,21 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    evals = int(run.ret.trace.objective_evals[W:W + K].sum())
-    trace_f = run.ret.trace.objective[:W + K].copy()
     run.info.close()
 
     # dominant kernel roofline (CUDA events on the launching stream, inside the timed region)
     peak, peak_src = peaks()
+    dom_per_eval = 2          # launches of the dominant kernel per fdf! (K_b + K_c)
     if args.workload == "rosenbrock":
         dom = "trial"
+        dom_per_eval = 1
         dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
         dom_ms, dom_cnt = timers["trial"]
     elif args.workload == "logreg":
         dom = "k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack)"
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]
         dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
-        d, N = n_local, int(n_local * LOGREG_SAMPLES_PER_FEATURE)
-        dom_bytes = (dom_cnt / 2.0) * ((12.0 * nnz_local + 8.0 * (N + 1)) + (12.0 * nnz_local + 8.0 * (d + 1))
-                                        + 40.0 * d + 24.0 * N)
+        dom_bytes = (dom_cnt / 2.0) * logreg_bytes(args, n_local, nnz_local)[1]
     else:
         dom = "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)"
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]
@@ -260,7 +309,7 @@ def run_ours(args):
                 "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
-                "kernel_share_of_step": round(dom_ms / ms, 4),
+                "kernel_share_of_step": round((dom_ms / max(dom_cnt, 1)) * dom_per_eval * evals / ms, 4),
                 "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}}
 
     # ---------------- end-to-end through the public API (`e2e`) ----------------
@@ -272,21 +321,28 @@ def run_ours(args):
         # warms the allocator, as a long-running host would have done
         cfg1, ls1 = solver_configs(cg, 1, args.workload)
         cg.minimizeobjective(obj, x0p, cfg1, ls1)
-        barrier()
-        t0 = time.perf_counter()
-        ret = cg.minimizeobjective(obj, x0p, cfg2, ls2)      # H2D x0 … K iterations … D2H x, g
-        barrier()
-        dt = time.perf_counter() - t0
+        remaining, dt, ev2, calls = K, 0.0, 0, 0
+        while remaining > 0:                                 # more than one call only if a run hits the FP64 floor
+            per_call = remaining if life is None else max(1, min(remaining, life - 3))
+            cfg2, ls2 = solver_configs(cg, per_call, args.workload)
+            barrier()
+            t0 = time.perf_counter()
+            ret = cg.minimizeobjective(obj, x0p, cfg2, ls2)  # H2D x0 … iterations … D2H x, g
+            barrier()
+            dt += time.perf_counter() - t0
+            assert ret.iters_ran > 0, (ret.iters_ran, ret.status)
+            remaining -= ret.iters_ran
+            ev2 += int(ret.trace.objective_evals.sum())
+            calls += 1
         tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         dt = float(tdt.item())
-        assert ret.iters_ran == K, (ret.iters_ran, ret.status)
-        ev2 = int(ret.trace.objective_evals.sum())
         e2e = {"value": round(K / dt, 4), "unit": "iterations/s",
-               "h2d_bytes_per_step": round((8.0 * n_local + 16.0 * (ev2 + K)) / K, 1),
-               "d2h_bytes_per_step": round((16.0 * n_local + 128.0 * (ev2 + 2 * K)) / K, 1),
+               "h2d_bytes_per_step": round((8.0 * n_local * calls + 16.0 * (ev2 + K)) / K, 1),
+               "d2h_bytes_per_step": round((16.0 * n_local * calls + 128.0 * (ev2 + 2 * K)) / K, 1),
+               "api_calls": calls,
                "includes": "x0 H2D from pinned host memory, f/g at x0, K iterations (scalar pack D2H "
                            "every launch), minimizer+gradient D2H", "wall_s": round(dt, 4)}
 
@@ -309,7 +365,7 @@ def run_ours(args):
                                     f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
                        "n": n, "sharding": f"rows/vector slices over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (vectors are 8n bytes >> 126 MB)",
-                       "fdf_evals_in_timed_region": evals, "host": "python/ctypes over the C ABI"},
+                       "fdf_evals_in_timed_region": evals, "restarts_in_timed_region": restarts, "host": "python/ctypes over the C ABI"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "host_wall_ms_per_step": round(wall_ms / K, 4),
             "objective_trace_head": [float(v) for v in trace_f[:4]],
@@ -431,7 +487,7 @@ def main():
         threads = os.cpu_count() or 1
         cb = run_cpu(args, max(args.steps, 1), min(args.warmup, 1), threads)
         n = args.n or FULL_N[args.workload]
-        line = {"impl": "reference", "metric": "cg_iterations_per_s", "value": round(cb["value"], 6),
+        line = {"impl": "reference", "metric": "lbfgs_iterations_per_s" if args.workload == "logreg" else "cg_iterations_per_s", "value": round(cb["value"], 6),
                 "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(1e3 / cb["value"], 3), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -245,6 +245,59 @@ struct AxpyDir {
     }
 };
 
+// Sample-sharded logistic regression (multi-rank): every rank's Aᵀ_r c_r partial gradient slice
+// of this rank's feature shard sits in q[r·stride ..]; add them in rank order, scale, add the
+// regulariser, and reduce the same eight dots as the single-rank SpMVᵀ epilogue (csr.cu EpiGrad).
+struct GradCombine {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 8;
+    static constexpr int OCC = 2;
+    struct In { double2 s, u, g, w; };
+    const double2 *q, *u, *g, *w;
+    double2 *gp;
+    int nparts;
+    int64_t stride2;            // part stride in double2 units
+    double invN, lambda;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t i) const {
+        In r;
+        r.s = cgo_ld2(q + i);
+        for (int p = 1; p < nparts; ++p) {
+            const double2 t = cgo_ld2(q + (int64_t)p * stride2 + i);
+            r.s.x = r.s.x + t.x;
+            r.s.y = r.s.y + t.y;
+        }
+        r.u = cgo_ld2(u + i); r.g = cgo_ld2(g + i); r.w = cgo_ld2(w + i);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t i, const In &in, double (&acc)[K], bool v2) const {
+        double2 gn;
+        gn.x = in.s.x * invN + lambda * in.w.x;
+        gn.y = v2 ? in.s.y * invN + lambda * in.w.y : 0.0;
+        cgo_st2(gp + i, gn);
+        const double ux = in.u.x, uy = v2 ? in.u.y : 0.0, gx = in.g.x, gy = v2 ? in.g.y : 0.0;
+        const double y1 = gn.x - gx, y2 = gn.y - gy;
+        acc[CGO_P_DPHI - 1] = acc[CGO_P_DPHI - 1] + gn.x * ux;
+        acc[CGO_P_GPGP - 1] = acc[CGO_P_GPGP - 1] + gn.x * gn.x;
+        acc[CGO_P_YY - 1] = acc[CGO_P_YY - 1] + y1 * y1;
+        acc[CGO_P_UY - 1] = acc[CGO_P_UY - 1] + ux * y1;
+        acc[CGO_P_YGP - 1] = acc[CGO_P_YGP - 1] + y1 * gn.x;
+        acc[CGO_P_GPG - 1] = acc[CGO_P_GPG - 1] + gn.x * gx;
+        acc[CGO_P_UG - 1] = acc[CGO_P_UG - 1] + ux * gx;
+        acc[CGO_P_UU - 1] = acc[CGO_P_UU - 1] + ux * ux;
+        if (v2) {
+            acc[CGO_P_DPHI - 1] = acc[CGO_P_DPHI - 1] + gn.y * uy;
+            acc[CGO_P_GPGP - 1] = acc[CGO_P_GPGP - 1] + gn.y * gn.y;
+            acc[CGO_P_YY - 1] = acc[CGO_P_YY - 1] + y2 * y2;
+            acc[CGO_P_UY - 1] = acc[CGO_P_UY - 1] + uy * y2;
+            acc[CGO_P_YGP - 1] = acc[CGO_P_YGP - 1] + y2 * gn.y;
+            acc[CGO_P_GPG - 1] = acc[CGO_P_GPG - 1] + gn.y * gy;
+            acc[CGO_P_UG - 1] = acc[CGO_P_UG - 1] + uy * gy;
+            acc[CGO_P_UU - 1] = acc[CGO_P_UU - 1] + uy * uy;
+        }
+    }
+};
+
 // L-BFGS: S = xp − x, Y = g⁺ − g; pack {s·y, y·y}
 struct LbfgsStage {
     static constexpr int TCLASS = CGO_T_LBFGS;
@@ -530,6 +583,14 @@ int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta) {
     op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
     op.xp = (double2 *)st->xp; op.a = a; op.beta = 0.0;
     return launch_blas1(st->ctx, op, st->n, red);
+}
+
+int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda) {
+    GradCombine op;
+    op.q = (const double2 *)q; op.u = (const double2 *)st->u; op.g = (const double2 *)st->g;
+    op.w = (const double2 *)st->xp; op.gp = (double2 *)st->gp;
+    op.nparts = nparts; op.stride2 = stride / 2; op.invN = invN; op.lambda = lambda;
+    return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx, CGO_P_DPHI));
 }
 
 // ------------------------------------------------------------------ L-BFGS

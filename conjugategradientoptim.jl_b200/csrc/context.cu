@@ -202,6 +202,45 @@ int cgo_sendrecv_ring(cgo_ctx *c, const double *send_to_prev, double *recv_from_
     return 0;
 }
 
+// all-gather of unequal contiguous shards: rank r owns [lo[r], lo[r+1]) of `full`; its own
+// shard is copied in from `mine`.  Grouped point-to-point transfers (NVLink through NVSwitch).
+int cgo_allgatherv_f64(cgo_ctx *c, const double *mine, double *full, const int64_t *lo) {
+    const int R = c->nranks, me = c->rank;
+    const int64_t cnt = lo[me + 1] - lo[me];
+    if (cnt > 0 && full + lo[me] != mine)
+        CGO_CUDA(cudaMemcpyAsync(full + lo[me], mine, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToDevice, c->stream));
+    if (R == 1) return 0;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    CGO_NCCL(g_nccl.GroupStart());
+    for (int k = 1; k < R; ++k) {
+        const int to = (me + k) % R, from = (me + R - k) % R;
+        if (cnt > 0) CGO_NCCL(g_nccl.Send(mine, (size_t)cnt, ncclFloat64, to, comm, c->stream));
+        if (lo[from + 1] > lo[from])
+            CGO_NCCL(g_nccl.Recv(full + lo[from], (size_t)(lo[from + 1] - lo[from]), ncclFloat64, from, comm, c->stream));
+    }
+    CGO_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+// all-to-all of shard slices: slice [lo[s], lo[s+1]) of `full` goes to rank s; the slice of MY
+// shard computed by rank s lands in recv + s * stride.
+int cgo_alltoallv_f64(cgo_ctx *c, const double *full, const int64_t *lo, double *recv, int64_t stride) {
+    const int R = c->nranks, me = c->rank;
+    const int64_t cnt = lo[me + 1] - lo[me];
+    if (cnt > 0)
+        CGO_CUDA(cudaMemcpyAsync(recv + (size_t)me * stride, full + lo[me], sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToDevice, c->stream));
+    if (R == 1) return 0;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    CGO_NCCL(g_nccl.GroupStart());
+    for (int k = 1; k < R; ++k) {
+        const int to = (me + k) % R, from = (me + R - k) % R;
+        if (lo[to + 1] > lo[to])
+            CGO_NCCL(g_nccl.Send(full + lo[to], (size_t)(lo[to + 1] - lo[to]), ncclFloat64, to, comm, c->stream));
+        if (cnt > 0) CGO_NCCL(g_nccl.Recv(recv + (size_t)from * stride, (size_t)cnt, ncclFloat64, from, comm, c->stream));
+    }
+    CGO_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
 // ------------------------------------------------------------------ per-launch timing
 static cudaEvent_t ev_get(cgo_ctx *c) {
     if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }

@@ -460,10 +460,12 @@ __global__ void k_ls_xtrue(LsSpec s, int64_t lo, int64_t nloc, int64_t halo, dou
         xt[e - halo] = 2.0 * g_u01(s.seed + 1, (uint64_t)i, 0) - 1.0;
     }
 }
-__global__ void k_lr_fill_A(LrSpec s, CsrMat A, double *label) {
-    GRID_STRIDE(i, s.N) {
-        const int64_t p = i * s.K;
-        A.rowptr[i] = p;
+// samples [i0, i0 + nloc) of the generator; column = global feature index
+__global__ void k_lr_fill_A(LrSpec s, int64_t i0, int64_t nloc, CsrMat A, double *label) {
+    GRID_STRIDE(il, nloc) {
+        const int64_t i = i0 + il;
+        const int64_t p = il * s.K;
+        A.rowptr[il] = p;
         double acc = 0.0;
         for (int k = 0; k < s.K; ++k) {
             int64_t c; double v;
@@ -474,8 +476,8 @@ __global__ void k_lr_fill_A(LrSpec s, CsrMat A, double *label) {
             acc += v * wt;
         }
         const double noise = 2.0 * g_u01(s.seed + 3, (uint64_t)i, 0) - 1.0;
-        label[i] = (acc + 0.1 * noise >= 0.0) ? 1.0 : -1.0;
-        if (i == s.N - 1) A.rowptr[s.N] = s.N * s.K;
+        label[il] = (acc + 0.1 * noise >= 0.0) ? 1.0 : -1.0;
+        if (il == nloc - 1) A.rowptr[nloc] = nloc * s.K;
     }
 }
 
@@ -667,10 +669,19 @@ struct CsrObj : cgo_obj {
     double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
     double lambda = 0.0;
     int64_t nsamples = 0;
+    // sample-sharded logistic regression (nranks > 1): A holds this rank's samples × all features,
+    // AT its transpose; the state vectors are feature shards [flo[rank], flo[rank+1])
+    bool lr_sharded = false;
+    std::vector<int64_t> flo;          // feature shard boundaries, nranks + 1
+    double *xp_full = nullptr;         // all-gathered trial point, n_global
+    double *g_part = nullptr;          // Aᵀ_r c_r, n_global
+    double *g_recv = nullptr;          // nranks × part_stride: every rank's slice of my shard
+    int64_t part_stride = 0;
     ~CsrObj() override {
         if (ctx) cudaSetDevice(ctx->device);
         csr_free(A); csr_free(AT);
         cudaFree(b); cudaFree(r_base);
+        cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
     }
     int alloc_r() {
         CGO_CUDA(cudaMalloc(&r_base, sizeof(double) * (size_t)(nrows + 2 * halo + 4)));
@@ -685,6 +696,20 @@ struct CsrObj : cgo_obj {
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
         CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                               // K_a
+        if (lr_sharded) {
+            // all-gather xp → margins of my samples → partial gradient over ALL features →
+            // all-to-all of shard slices → rank-ordered combine fused with the dot pack
+            CGO_TRY(cgo_allgatherv_f64(ctx, st->xp, xp_full, flo.data()));
+            EpiLogit e1{b, r};
+            CGO_TRY(launch_csr(ctx, A, xp_full, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));  // K_b
+            EpiStore e2{g_part};
+            CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_SPMVT)); // K_c
+            CGO_TRY(cgo_alltoallv_f64(ctx, g_part, flo.data(), g_recv, part_stride));
+            CGO_TRY(cgo_blas1_grad_combine(st, g_recv, ctx->nranks, part_stride, 1.0 / (double)nsamples, lambda));
+            CGO_TRY(cgo_finish_pack(ctx, 12, out));
+            out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
+            return 0;
+        }
         CGO_TRY(exchange(st->xp, st->n));
         if (logreg) {
             EpiLogit e1{b, r};
@@ -707,6 +732,9 @@ struct CsrObj : cgo_obj {
     // A and Aᵀ streamed once (8 B value + 4 B index per entry + row pointers)
     // plus the vector passes R x,u W xp | gather xp, R b, W r | gather r, W g⁺, R u (,g)
     double bytes_per_eval() const override {
+        if (lr_sharded)     // K_a 24d_loc | A_r + gather + R y W c | Aᵀ_r + gather + W part (d) | combine R parts,u,g,w W g⁺
+            return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
+                   8.0 * (3.0 * (double)nrows + 2.0 * (double)n_global + (8.0 + (double)ctx->nranks) * (double)n_local);
         return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
                8.0 * (3.0 * (double)nrows + 6.0 * (double)n_local);
     }
@@ -821,24 +849,48 @@ extern "C" int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t
 extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t d, int32_t K, uint64_t seed,
                                                double lambda, cgo_obj **out) {
     CGO_CHECK(ctx && out, "NULL argument");
-    CGO_CHECK(ctx->nranks == 1, "cgo_obj_logreg_create_synthetic is single-GPU in this version");
     CGO_CHECK(K >= 1 && N >= 1 && d >= K, "logreg: need nnz_per_row >= 1, nsamples >= 1, nfeat >= nnz_per_row");
+    const int R = ctx->nranks;
+    CGO_CHECK(R == 1 || (N >= 2 * R && d >= 2 * R), "logreg: %d ranks need nsamples >= %d and nfeat >= %d", R, 2 * R, 2 * R);
     CGO_CUDA(cudaSetDevice(ctx->device));
     CsrObj *o = new CsrObj();
     o->ctx = ctx; o->logreg = true; o->lambda = lambda; o->nsamples = N;
-    o->n_global = d; o->n_local = d; o->offset = 0; o->nrows = N; o->halo = 0;
+    o->n_global = d; o->halo = 0;
+    // samples (rows of A) and features (state vectors) are both sharded contiguously
+    int64_t slo = 0, shi = N;
+    o->flo.assign(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        int64_t lo, hi;
+        CGO_TRY(cgo_shard_range(d, R, r, 2, &lo, &hi));
+        o->flo[r] = lo; o->flo[r + 1] = hi;
+        if (hi - lo > o->part_stride) o->part_stride = hi - lo;
+    }
+    o->part_stride = (o->part_stride + 3) & ~(int64_t)1;          // even, with one element of slack
+    CGO_TRY(cgo_shard_range(N, R, ctx->rank, 2, &slo, &shi));
+    o->offset = o->flo[ctx->rank]; o->n_local = o->flo[ctx->rank + 1] - o->flo[ctx->rank];
+    o->nrows = shi - slo;
+    o->lr_sharded = R > 1;
     LrSpec sp;
     sp.N = N; sp.d = d; sp.K = K; sp.w = d / K; sp.seed = seed;
+    const int64_t nloc = o->nrows;
     auto body = [&]() -> int {
-        CGO_TRY(check_i32(N > d ? N : d, "matrix dimension"));
-        CGO_TRY(csr_alloc(o->A, N, N * K));
-        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(N + CSR_PAD)));
-        k_lr_fill_A<<<grid_for(N, ctx->sms), 256, 0, ctx->stream>>>(sp, o->A, o->b);
+        CGO_TRY(check_i32(nloc > d ? nloc : d, "matrix dimension"));
+        CGO_TRY(csr_alloc(o->A, nloc, nloc * K));
+        CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(nloc + CSR_PAD)));
+        k_lr_fill_A<<<grid_for(nloc, ctx->sms), 256, 0, ctx->stream>>>(sp, slo, nloc, o->A, o->b);
         CGO_CUDA(cudaGetLastError());
         CGO_TRY(o->alloc_r());
-        CsrSrc src{o->A.col, N * K};
+        CsrSrc src{o->A.col, nloc * K};
         FixedKFin fin{K, o->A.val};
         CGO_TRY(build_transpose(ctx, src, fin, d, o->AT));
+        if (o->lr_sharded) {
+            CGO_CUDA(cudaMalloc(&o->xp_full, sizeof(double) * (size_t)(d + CSR_PAD)));
+            CGO_CUDA(cudaMalloc(&o->g_part, sizeof(double) * (size_t)(d + CSR_PAD)));
+            CGO_CUDA(cudaMalloc(&o->g_recv, sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD)));
+            CGO_CUDA(cudaMemsetAsync(o->xp_full, 0, sizeof(double) * (size_t)(d + CSR_PAD), ctx->stream));
+            CGO_CUDA(cudaMemsetAsync(o->g_recv, 0, sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD), ctx->stream));
+            CGO_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         return 0;
     };
     int rc = body();
@@ -875,7 +927,7 @@ extern "C" int cgo_obj_csr_download(cgo_obj *obj, int transposed, int64_t *rowpt
 extern "C" int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, double *y_host) {
     CsrObj *o = as_csr(obj);
     CGO_CHECK(o && x_host && y_host, "not a CSR objective / NULL argument");
-    CGO_CHECK(o->halo == 0, "cgo_obj_spmv is a single-GPU test hook");
+    CGO_CHECK(o->halo == 0 && !o->lr_sharded, "cgo_obj_spmv is a single-GPU test hook");
     cgo_ctx *c = o->ctx;
     CGO_CUDA(cudaSetDevice(c->device));
     const CsrMat &M = transposed ? o->AT : o->A;

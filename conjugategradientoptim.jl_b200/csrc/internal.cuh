@@ -92,6 +92,8 @@ int cgo_finish_pack(cgo_ctx *ctx, int K, double *out_host);
 int cgo_allgather_bytes(cgo_ctx *ctx, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
 int cgo_sendrecv_ring(cgo_ctx *ctx, const double *send_to_prev, double *recv_from_next,
                       const double *send_to_next, double *recv_from_prev, int64_t count);
+int cgo_allgatherv_f64(cgo_ctx *ctx, const double *mine, double *full, const int64_t *lo);
+int cgo_alltoallv_f64(cgo_ctx *ctx, const double *full, const int64_t *lo, double *recv, int64_t stride);
 
 // ------------------------------------------------------------------ objective interface
 struct cgo_state;
@@ -127,6 +129,9 @@ struct cgo_state {
 // xp = x + a u (optionally after u = −g + βu); {g·u, u·u, xp·xp} land in pack slots
 // CGO_P_DIR_GU, CGO_P_DIR_UU, CGO_P_XPXP
 int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta);
+// sample-sharded logistic regression: g⁺ = (Σ_r q[r·stride + i]) / N + λ xp, partial gradients
+// added in rank order, fused with the dot pack of EpiGrad (slots CGO_P_DPHI .. CGO_P_UU)
+int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda);
 
 // ------------------------------------------------------------------ CSR (csr.cu)
 struct CsrMat {

@@ -115,7 +115,10 @@ int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n_global, int32_t n
 int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t ncols, const int64_t *rowptr,
                                  const int32_t *col, const double *val, const double *b,
                                  cgo_obj **out);
-/* (1/N) Σ log(1 + exp(−y_i a_i·w)) + (λ/2)‖w‖², synthetic CSR, single GPU */
+/* (1/N) Σ log(1 + exp(−y_i a_i·w)) + (λ/2)‖w‖², synthetic CSR.  With R ranks the samples (rows of A)
+ * and the features (state vectors) are both sharded contiguously (cgo_shard_range, align 2): per
+ * trial the shards of xp are all-gathered, every rank forms Aᵀ_r c_r over all features, the shard
+ * slices are exchanged all-to-all and added in rank order (deterministic for a fixed R). */
 int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t nsamples, int64_t nfeat,
                                     int32_t nnz_per_row, uint64_t seed, double lambda,
                                     cgo_obj **out);

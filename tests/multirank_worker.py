@@ -55,6 +55,29 @@ def main():
             obj = cg.SparseLSGPU(n, 10, 2048, 24, coh, ctx)
             check(f"sparse_ls coh={coh}", obj, np.zeros(n), O.Objective.sparse_ls(n, 10, 2048, 24, coh), flavour, 60)
             obj.close()
+    # cfg 4 (BASELINE.json configs[3]): sample-sharded logistic regression + L-BFGS.  exp / log1p
+    # differ from glibc in the last ulp and the gradient partials are added shard by shard, so the
+    # comparison is at north_star's tolerances with identical line-search decisions.
+    N, d, lam = 20_000, 2002, 1e-4
+    for flavour in ("LBFGS", "HagerZhang"):
+        ocfg, cfg, ls = make_pair(flavour, eps=1e-6, max_iters=60, c1=1e-4, c2=0.9, lbfgs_m=10)
+        obj = cg.LogRegGPU(N, d, 20, 24, lam, ctx)
+        lo, hi = obj.offset, obj.offset + obj.n_local
+        assert (lo, hi) == cg.shard_range(d, world, rank, 2) and obj.n_global == d
+        ret = cg.minimizeobjective(obj, np.zeros(hi - lo), cfg, ls)
+        ora = O.minimize(O.Objective.logreg(N, d, 20, 24, lam), np.zeros(d), ocfg)
+        k = min(50, len(ora.trace_objective), len(ret.trace.objective))
+        ok = (k >= 10 and ret.status == ora.status and abs(ret.iters_ran - ora.iters_ran) <= 2
+              and np.array_equal(ret.trace.step_size[:k], ora.trace_step_size[:k])
+              and np.array_equal(ret.trace.objective_evals[:k], ora.trace_objective_evals[:k])
+              and np.allclose(ret.trace.objective[:k], ora.trace_objective[:k], rtol=1e-10, atol=0)
+              and np.allclose(ret.trace.grad_norm[:k], ora.trace_grad_norm[:k], rtol=1e-8, atol=0)
+              and abs(ret.objective - ora.objective) <= 1e-8 * abs(ora.objective)
+              and np.allclose(ret.minimizer, ora.minimizer[lo:hi], rtol=1e-6, atol=1e-9))
+        if not ok:
+            fails.append(f"logreg/{flavour}: rank {rank} status {ret.status}/{ora.status} iters {ret.iters_ran}/{ora.iters_ran} "
+                         f"f {ret.objective!r}/{ora.objective!r} k={k}")
+        obj.close()
     ctx.barrier()
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
