@@ -292,10 +292,13 @@ def run_ours(args):
         dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
         dom_ms, dom_cnt = timers["trial"]
     elif args.workload == "logreg":
-        dom = "k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack)"
+        dom = ("k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack), one pass per "
+               "L2-sized column block of the gathered vector")
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]
         dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
-        dom_bytes = (dom_cnt / 2.0) * logreg_bytes(args, n_local, nnz_local)[1]
+        n_evals = timers["axpy"][1]          # one K_a per fdf!; K_b / K_c may take several column-block passes
+        dom_bytes = n_evals * logreg_bytes(args, n_local, nnz_local)[1]
+        dom_per_eval = dom_cnt / max(n_evals, 1)
     else:
         dom = "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)"
         dom_ms = timers["spmv"][0] + timers["spmvT"][0]

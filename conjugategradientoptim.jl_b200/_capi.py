@@ -42,6 +42,7 @@ _SIGS = {
     "cgo_ctx_destroy": (C.c_int, [_vp]),
     "cgo_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "cgo_ctx_set_reduction_ctas": (C.c_int, [_vp, C.c_int]),
+    "cgo_ctx_set_gather_block_bytes": (C.c_int, [_vp, C.c_int64]),
     "cgo_ctx_sm_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cgo_ctx_kernel_launches": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_timing": (C.c_int, [_vp, C.c_int]),
@@ -61,6 +62,7 @@ _SIGS = {
     "cgo_obj_bytes_per_eval": (C.c_int, [_vp, _dp]),
     "cgo_obj_default_x0": (C.c_int, [_vp, C.c_uint64, C.c_double, _dp]),
     "cgo_obj_csr_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cgo_obj_csr_blocks": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int32)]),
     "cgo_obj_csr_download": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
     "cgo_obj_spmv": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "cgo_state_create": (C.c_int, [_vp, _vp, _dp, C.c_int32, C.POINTER(_vp), _dp]),

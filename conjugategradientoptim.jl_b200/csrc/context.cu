@@ -116,6 +116,12 @@ extern "C" int cgo_ctx_set_reduction_ctas(cgo_ctx *c, int G) {
     c->G = G;
     return 0;
 }
+extern "C" int cgo_ctx_set_gather_block_bytes(cgo_ctx *c, int64_t bytes) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CHECK(bytes >= 0, "cgo_ctx_set_gather_block_bytes: negative size");
+    c->gather_block_bytes = (size_t)bytes;
+    return 0;
+}
 extern "C" int cgo_ctx_sm_count(cgo_ctx *c, int *sms) {
     CGO_CHECK(c && sms, "NULL argument");
     *sms = c->sms;

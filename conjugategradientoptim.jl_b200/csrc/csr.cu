@@ -241,6 +241,7 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
                     if (valid) {
                         rs = rp[tid]; re = rp[tid + 1];
                         pre = epi.load(reinterpret_cast<const double *>(desc + L::RP_BYTES), tid);
+                        if (Epi::HAS_INIT) sum = epi.init(pre);     // column-blocked pass: continue the row sum
                     }
                     p0 = rp[0];
                     p1 = rp[nvalid];
@@ -308,7 +309,9 @@ static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &
 // row sum is known.
 struct EpiStore {                       // y = A x
     static constexpr int K = 1, NOPS = 0;
+    static constexpr bool HAS_INIT = false;
     struct Pre {};
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
     double *y;
     __device__ __forceinline__ const double *operand(int) const { return nullptr; }
     __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
@@ -316,7 +319,9 @@ struct EpiStore {                       // y = A x
 };
 struct EpiResidual {                    // r = A xp − b ; Σ r²
     static constexpr int K = 1, NOPS = 1;
+    static constexpr bool HAS_INIT = false;
     struct Pre { double b; };
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
     const double *b;
     double *r;
     __device__ __forceinline__ const double *operand(int) const { return b; }
@@ -332,7 +337,9 @@ struct EpiResidual {                    // r = A xp − b ; Σ r²
 template <bool LOGREG>
 struct EpiGrad {
     static constexpr int K = 8, NOPS = LOGREG ? 3 : 2;
+    static constexpr bool HAS_INIT = false;
     struct Pre { double u, g, w; };
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
     double *gp;
     const double *g, *u, *w;
     double invN, lambda;
@@ -363,7 +370,9 @@ struct EpiGrad {
 //   t = −y z; e = exp(−|t|); ℓ = max(t,0) + log1p(e); σ = t ≥ 0 ? 1/(1+e) : e/(1+e); c = −y σ
 struct EpiLogit {
     static constexpr int K = 1, NOPS = 1;
+    static constexpr bool HAS_INIT = false;
     struct Pre { double y; };
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
     const double *label;
     double *c;
     __device__ __forceinline__ const double *operand(int) const { return label; }
@@ -378,6 +387,35 @@ struct EpiLogit {
         acc[0] = acc[0] + l;
     }
 };
+
+// Column-blocked matrices (CsrBlocked below): pass j > 0 of a row continues the sum pass j − 1
+// left in `partial` (one more staged operand), so the products of a row are still added one by one
+// in storage order — bit-identical to the single-pass kernel.
+template <class Base>
+struct WithInit : Base {
+    static constexpr int K = Base::K, NOPS = Base::NOPS + 1;
+    static constexpr bool HAS_INIT = true;
+    struct Pre { typename Base::Pre base; double init; };
+    const double *partial;
+    __device__ __forceinline__ const double *operand(int o) const { return o < Base::NOPS ? Base::operand(o) : partial; }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const {
+        Pre p;
+        p.base = Base::load(ops, t);
+        p.init = ops[Base::NOPS * CGO_B + t];
+        return p;
+    }
+    __device__ __forceinline__ double init(const Pre &p) const { return p.init; }
+    __device__ __forceinline__ void row(int64_t i, double sum, const Pre &p, double (&acc)[K]) const {
+        Base::row(i, sum, p.base, acc);
+    }
+};
+template <class Base>
+static WithInit<Base> with_init(const Base &b, const double *partial) {
+    WithInit<Base> w;
+    static_cast<Base &>(w) = b;
+    w.partial = partial;
+    return w;
+}
 
 // ------------------------------------------------------------------ counter-based hash
 // (generator spec: oracle/cgo_oracle.c hash3 / u01; restated, identical arithmetic)
@@ -660,10 +698,114 @@ static int build_transpose(cgo_ctx *c, const Src &src, const Fin &fin, int64_t n
     return rc;
 }
 
+// ------------------------------------------------------------------ column blocking (setup)
+// A gather that ranges over more than about half of the 126 MB L2 (measured cliff: 48 MB still
+// hits, 60 MB starts missing) turns every 8-byte gather into a 32-byte DRAM sector read.  For
+// such matrices the columns are cut into nb blocks of at most ctx->gather_block_bytes and the
+// matrix is stored block-major: blk[j] holds the entries of every row whose column lies in block
+// j (rows' columns must ascend, which both logistic-regression matrices do by construction).  One
+// pass per block keeps its window of the gathered vector L2-resident; passes chain the row sums
+// (WithInit), so the arithmetic order is unchanged.
+struct CsrBlocked {
+    std::vector<CsrMat> blk;
+    void free_all() { for (auto &m : blk) csr_free(m); blk.clear(); }
+};
+__global__ void k_blk_check_sorted(CsrMat A, int *bad) {
+    GRID_STRIDE(i, A.nrows) {
+        for (int64_t p = A.rowptr[i] + 1; p < A.rowptr[i + 1]; ++p)
+            if (A.col[p] < A.col[p - 1]) { *bad = 1; break; }
+    }
+}
+// entries of row i with c0 <= col < c1: first[i] = their start in A, cnt[i] = how many
+__global__ void k_blk_count(CsrMat A, int32_t c0, int32_t c1, int64_t *first, int64_t *cnt) {
+    GRID_STRIDE(i, A.nrows + 1) {
+        if (i == A.nrows) { cnt[i] = 0; continue; }
+        const int64_t rs = A.rowptr[i], re = A.rowptr[i + 1];
+        int64_t lo = rs, hi = re;                // lower_bound(c0)
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (A.col[mid] < c0) lo = mid + 1; else hi = mid; }
+        const int64_t b0 = lo;
+        hi = re;                                 // lower_bound(c1)
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (A.col[mid] < c1) lo = mid + 1; else hi = mid; }
+        first[i] = b0;
+        cnt[i] = lo - b0;
+    }
+}
+__global__ void k_blk_copy(CsrMat A, const int64_t *first, CsrMat B) {
+    GRID_STRIDE(i, A.nrows) {
+        const int64_t d0 = B.rowptr[i], n = B.rowptr[i + 1] - d0, s0 = first[i];
+        for (int64_t e = 0; e < n; ++e) { B.col[d0 + e] = A.col[s0 + e]; B.val[d0 + e] = A.val[s0 + e]; }
+    }
+}
+static int build_blocked(cgo_ctx *c, const CsrMat &A, int64_t ncols, CsrBlocked &out) {
+    out.free_all();
+    const int64_t cap = (int64_t)(c->gather_block_bytes / sizeof(double));
+    if (cap <= 0 || ncols <= cap || A.nnz == 0) return 0;
+    const int64_t nb = (ncols + cap - 1) / cap;
+    const int64_t bc = (((ncols + nb - 1) / nb) + 1) & ~(int64_t)1;
+    cudaStream_t s = c->stream;
+    int *bad = nullptr;
+    int64_t *first = nullptr, *cnt = nullptr;
+    void *tmp = nullptr;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&bad, sizeof(int)));
+        CGO_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+        k_blk_check_sorted<<<grid_for(A.nrows, c->sms), 256, 0, s>>>(A, bad);
+        int hbad = 0;
+        CGO_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CGO_CUDA(cudaStreamSynchronize(s));
+        if (hbad) return 0;                      // columns not ascending: stay single-pass
+        CGO_CUDA(cudaMalloc(&first, sizeof(int64_t) * (size_t)(A.nrows + 1)));
+        CGO_CUDA(cudaMalloc(&cnt, sizeof(int64_t) * (size_t)(A.nrows + 1)));
+        size_t tmp_bytes = 0;
+        CGO_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, cnt, A.nrows + 1, s));
+        CGO_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+        out.blk.resize((size_t)nb);
+        for (int64_t j = 0; j < nb; ++j) {
+            CsrMat &B = out.blk[(size_t)j];
+            const int64_t c0 = j * bc, c1 = (j + 1) * bc < ncols ? (j + 1) * bc : ncols;
+            k_blk_count<<<grid_for(A.nrows + 1, c->sms), 256, 0, s>>>(A, (int32_t)c0, (int32_t)c1, first, cnt);
+            CGO_CUDA(cudaGetLastError());
+            B.nrows = A.nrows;
+            CGO_CUDA(cudaMalloc(&B.rowptr, sizeof(int64_t) * (size_t)(A.nrows + 1 + CSR_PAD)));
+            CGO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, B.rowptr, A.nrows + 1, s));
+            int64_t nnzb = 0;
+            CGO_CUDA(cudaMemcpyAsync(&nnzb, B.rowptr + A.nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CGO_CUDA(cudaStreamSynchronize(s));
+            B.nnz = nnzb;
+            CGO_CUDA(cudaMalloc(&B.col, sizeof(int32_t) * (size_t)(nnzb + CSR_PAD)));
+            CGO_CUDA(cudaMalloc(&B.val, sizeof(double) * (size_t)(nnzb + CSR_PAD)));
+            k_blk_copy<<<grid_for(A.nrows, c->sms), 256, 0, s>>>(A, first, B);
+            CGO_CUDA(cudaGetLastError());
+        }
+        CGO_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    };
+    int rc = body();
+    cudaFree(bad); cudaFree(first); cudaFree(cnt); cudaFree(tmp);
+    if (rc) out.free_all();
+    return rc;
+}
+// one pass per column block; the last pass runs the real epilogue
+template <class Epi>
+static int launch_csr_blocked(cgo_ctx *c, const CsrMat &A, const CsrBlocked &B, const double *xg, const Epi &epi,
+                              double *partial, const RedArgs &red, int tclass) {
+    if (B.blk.empty()) return launch_csr(c, A, xg, epi, red, tclass);
+    const size_t nb = B.blk.size();
+    const RedArgs scratch = cgo_red_args(c, CGO_PACK_LEN - 1);
+    for (size_t j = 0; j + 1 < nb; ++j) {
+        EpiStore es{partial};
+        if (j == 0) CGO_TRY(launch_csr(c, B.blk[j], xg, es, scratch, tclass));
+        else CGO_TRY(launch_csr(c, B.blk[j], xg, with_init(es, partial), scratch, tclass));
+    }
+    return launch_csr(c, B.blk[nb - 1], xg, with_init(epi, partial), red, tclass);
+}
+
 // ------------------------------------------------------------------ the objective
 struct CsrObj : cgo_obj {
     bool logreg = false;
     CsrMat A, AT;
+    CsrBlocked Ab, ATb;                // column-blocked copies (logreg, large gather ranges)
+    bool have_unblocked = true;        // A / AT arrays still allocated (test hooks need them)
     int64_t nrows = 0;                 // local rows of A (residuals / samples)
     double *b = nullptr;               // rhs (LS) or labels (logreg), nrows
     double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
@@ -680,6 +822,7 @@ struct CsrObj : cgo_obj {
     ~CsrObj() override {
         if (ctx) cudaSetDevice(ctx->device);
         csr_free(A); csr_free(AT);
+        Ab.free_all(); ATb.free_all();
         cudaFree(b); cudaFree(r_base);
         cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
     }
@@ -701,9 +844,9 @@ struct CsrObj : cgo_obj {
             // all-to-all of shard slices → rank-ordered combine fused with the dot pack
             CGO_TRY(cgo_allgatherv_f64(ctx, st->xp, xp_full, flo.data()));
             EpiLogit e1{b, r};
-            CGO_TRY(launch_csr(ctx, A, xp_full, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));  // K_b
+            CGO_TRY(launch_csr_blocked(ctx, A, Ab, xp_full, e1, r, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));  // K_b
             EpiStore e2{g_part};
-            CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_SPMVT)); // K_c
+            CGO_TRY(launch_csr_blocked(ctx, AT, ATb, r, e2, g_part, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_SPMVT)); // K_c
             CGO_TRY(cgo_alltoallv_f64(ctx, g_part, flo.data(), g_recv, part_stride));
             CGO_TRY(cgo_blas1_grad_combine(st, g_recv, ctx->nranks, part_stride, 1.0 / (double)nsamples, lambda));
             CGO_TRY(cgo_finish_pack(ctx, 12, out));
@@ -713,9 +856,9 @@ struct CsrObj : cgo_obj {
         CGO_TRY(exchange(st->xp, st->n));
         if (logreg) {
             EpiLogit e1{b, r};
-            CGO_TRY(launch_csr(ctx, A, st->xp, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));   // K_b
+            CGO_TRY(launch_csr_blocked(ctx, A, Ab, st->xp, e1, r, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));   // K_b
             EpiGrad<true> e2{st->gp, st->g, st->u, st->xp, 1.0 / (double)nsamples, lambda};
-            CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT));      // K_c
+            CGO_TRY(launch_csr_blocked(ctx, AT, ATb, r, e2, st->gp, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT)); // K_c
             CGO_TRY(cgo_finish_pack(ctx, 12, out));
             out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
         } else {
@@ -883,6 +1026,15 @@ extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t 
         CsrSrc src{o->A.col, nloc * K};
         FixedKFin fin{K, o->A.val};
         CGO_TRY(build_transpose(ctx, src, fin, d, o->AT));
+        // K_b gathers over all d features, K_c over this rank's samples
+        CGO_TRY(build_blocked(ctx, o->A, d, o->Ab));
+        CGO_TRY(build_blocked(ctx, o->AT, nloc, o->ATb));
+        if ((!o->Ab.blk.empty() || !o->ATb.blk.empty()) && o->A.nnz > (int64_t)200000000) {
+            // production sizes: drop the single-pass copies (only the CSR test hooks read them)
+            if (!o->Ab.blk.empty()) { cudaFree(o->A.col); cudaFree(o->A.val); o->A.col = nullptr; o->A.val = nullptr; }
+            if (!o->ATb.blk.empty()) { cudaFree(o->AT.col); cudaFree(o->AT.val); o->AT.col = nullptr; o->AT.val = nullptr; }
+            o->have_unblocked = false;
+        }
         if (o->lr_sharded) {
             CGO_CUDA(cudaMalloc(&o->xp_full, sizeof(double) * (size_t)(d + CSR_PAD)));
             CGO_CUDA(cudaMalloc(&o->g_part, sizeof(double) * (size_t)(d + CSR_PAD)));
@@ -902,6 +1054,13 @@ extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t 
 // ------------------------------------------------------------------ test hooks
 static CsrObj *as_csr(cgo_obj *o) { return dynamic_cast<CsrObj *>(o); }
 
+extern "C" int cgo_obj_csr_blocks(cgo_obj *obj, int transposed, int32_t *nblocks) {
+    CsrObj *o = as_csr(obj);
+    CGO_CHECK(o && nblocks, "not a CSR objective / NULL argument");
+    const CsrBlocked &B = transposed ? o->ATb : o->Ab;
+    *nblocks = B.blk.empty() ? 1 : (int32_t)B.blk.size();
+    return 0;
+}
 extern "C" int cgo_obj_csr_nnz(cgo_obj *obj, int transposed, int64_t *nrows, int64_t *nnz) {
     CsrObj *o = as_csr(obj);
     CGO_CHECK(o != nullptr, "not a CSR objective");
@@ -913,6 +1072,7 @@ extern "C" int cgo_obj_csr_nnz(cgo_obj *obj, int transposed, int64_t *nrows, int
 extern "C" int cgo_obj_csr_download(cgo_obj *obj, int transposed, int64_t *rowptr, int32_t *col, double *val, double *b) {
     CsrObj *o = as_csr(obj);
     CGO_CHECK(o != nullptr, "not a CSR objective");
+    CGO_CHECK(o->have_unblocked, "the single-pass CSR copy was dropped at this size (column-blocked storage only)");
     const CsrMat &M = transposed ? o->AT : o->A;
     cudaStream_t s = o->ctx->stream;
     CGO_CUDA(cudaSetDevice(o->ctx->device));
@@ -928,6 +1088,7 @@ extern "C" int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, 
     CsrObj *o = as_csr(obj);
     CGO_CHECK(o && x_host && y_host, "not a CSR objective / NULL argument");
     CGO_CHECK(o->halo == 0 && !o->lr_sharded, "cgo_obj_spmv is a single-GPU test hook");
+    CGO_CHECK(o->have_unblocked, "the single-pass CSR copy was dropped at this size (column-blocked storage only)");
     cgo_ctx *c = o->ctx;
     CGO_CUDA(cudaSetDevice(c->device));
     const CsrMat &M = transposed ? o->AT : o->A;

@@ -57,6 +57,7 @@ struct cgo_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int G = 296;
+    size_t gather_block_bytes = (size_t)40 << 20;   // column-block size of large random gathers (csr.cu)
     int64_t launches = 0;
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax

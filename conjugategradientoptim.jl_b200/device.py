@@ -37,6 +37,10 @@ class Context:
     def set_reduction_ctas(self, G: int):
         check(lib().cgo_ctx_set_reduction_ctas(self.h, G))
 
+    def set_gather_block_bytes(self, nbytes: int):
+        """Column-block size for objectives with large random gathers (0 disables blocking)."""
+        check(lib().cgo_ctx_set_gather_block_bytes(self.h, int(nbytes)))
+
     @property
     def stream_ptr(self) -> int:
         s = C.c_void_p()
@@ -156,6 +160,12 @@ class DeviceObjective:
         check(lib().cgo_obj_csr_download(self.h, int(transposed), rp.ctypes.data, ci.ctypes.data,
                                          va.ctypes.data, b.ctypes.data))
         return rp, ci, va, b
+
+    def csr_blocks(self, transposed=False) -> int:
+        """passes one SpMV with this matrix takes (1 = not column-blocked)"""
+        v = C.c_int32()
+        check(lib().cgo_obj_csr_blocks(self.h, int(transposed), C.byref(v)))
+        return v.value
 
     def spmv(self, x, transposed=False):
         nr, nnz = C.c_int64(), C.c_int64()

@@ -84,6 +84,10 @@ int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out);
 int cgo_ctx_destroy(cgo_ctx *ctx);
 int cgo_ctx_stream(cgo_ctx *ctx, void **cuda_stream_out);
 int cgo_ctx_set_reduction_ctas(cgo_ctx *ctx, int G);        /* canonical-order G (default 296) */
+/* objectives whose gathers range over a vector larger than this are stored column-blocked and
+ * evaluated one block per pass, so that the gathered window stays L2-resident (default 40 MiB;
+ * 0 = never block).  Applies to objectives created afterwards; results are bit-identical. */
+int cgo_ctx_set_gather_block_bytes(cgo_ctx *ctx, int64_t bytes);
 int cgo_ctx_sm_count(cgo_ctx *ctx, int *sms);
 int cgo_ctx_kernel_launches(cgo_ctx *ctx, int64_t *count);  /* kernels launched so far */
 /* optional per-launch CUDA-event timing on the ctx stream, by kernel class:
@@ -129,6 +133,7 @@ int cgo_obj_bytes_per_eval(cgo_obj *obj, double *bytes);   /* algorithmic HBM by
 int cgo_obj_default_x0(cgo_obj *obj, uint64_t seed, double perturb, double *x0_host);
 /* test hooks: CSR download (transposed = 0/1) and y = A x / Aᵀ x on device, single GPU */
 int cgo_obj_csr_nnz(cgo_obj *obj, int transposed, int64_t *nrows, int64_t *nnz);
+int cgo_obj_csr_blocks(cgo_obj *obj, int transposed, int32_t *nblocks);   /* passes per SpMV (1 = unblocked) */
 int cgo_obj_csr_download(cgo_obj *obj, int transposed, int64_t *rowptr, int32_t *col, double *val,
                          double *b);
 int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, double *y_host);

@@ -61,7 +61,9 @@ def main():
     N, d, lam = 20_000, 2002, 1e-4
     for flavour in ("LBFGS", "HagerZhang"):
         ocfg, cfg, ls = make_pair(flavour, eps=1e-6, max_iters=60, c1=1e-4, c2=0.9, lbfgs_m=10)
+        ctx.set_gather_block_bytes(8 * 600 if flavour == "HagerZhang" else 40 << 20)   # also the column-blocked passes
         obj = cg.LogRegGPU(N, d, 20, 24, lam, ctx)
+        assert (obj.csr_blocks(False) > 1) == (flavour == "HagerZhang")
         lo, hi = obj.offset, obj.offset + obj.n_local
         assert (lo, hi) == cg.shard_range(d, world, rank, 2) and obj.n_global == d
         ret = cg.minimizeobjective(obj, np.zeros(hi - lo), cfg, ls)

@@ -98,3 +98,27 @@ def test_run_to_run_reproducible(ctx):
     b = cg.minimizeobjective(obj, np.zeros(d), cfg, ls)
     assert np.array_equal(a.trace.objective, b.trace.objective) and np.array_equal(a.minimizer, b.minimizer)
     obj.close()
+
+
+@pytest.mark.parametrize("block_elems", [700, 64, 2999])
+def test_column_blocked_passes_are_bit_identical(block_elems):
+    """Large random gathers are evaluated one L2-sized column block per pass (csr.cu CsrBlocked);
+    passes chain the row sums, so f, g and whole runs must not change by a single bit."""
+    N, d, lam = 20_000, 3000, 1e-4
+    c0, c1 = cg.Context(0), cg.Context(0)
+    c0.set_gather_block_bytes(0)
+    c1.set_gather_block_bytes(8 * block_elems)
+    a, b = cg.LogRegGPU(N, d, 20, 24, lam, c0), cg.LogRegGPU(N, d, 20, 24, lam, c1)
+    assert a.csr_blocks(False) == 1 and a.csr_blocks(True) == 1
+    assert b.csr_blocks(False) == -(-d // block_elems) and b.csr_blocks(True) == -(-N // block_elems)
+    w = 0.5 * np.random.default_rng(3).standard_normal(d)
+    wa, wb = a.make_workspace(w, fuse_direction=False), b.make_workspace(w, fuse_direction=False)
+    assert wa.f_x0 == wb.f_x0 and np.array_equal(wa.pack, wb.pack)
+    assert np.array_equal(wa.download()[1], wb.download()[1])
+    wa.close(); wb.close()
+    _, cfg, ls = make_pair("LBFGS", max_iters=25, c1=1e-4, c2=0.9)
+    ra = cg.minimizeobjective(a, np.zeros(d), cfg, ls)
+    rb = cg.minimizeobjective(b, np.zeros(d), cfg, ls)
+    assert ra.status == rb.status and np.array_equal(ra.trace.objective, rb.trace.objective)
+    assert np.array_equal(ra.trace.step_size, rb.trace.step_size) and np.array_equal(ra.minimizer, rb.minimizer)
+    a.close(); b.close(); c0.close(); c1.close()
