@@ -62,26 +62,86 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
+    (5 ms period, so that even a 30 ms region gets samples); falls back to an `nvidia-smi -lms`
+    subprocess when pynvml is unavailable.  Only samples taken between mark_begin() and mark_end()
+    count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = self.thread = None
+        self.samples = []               # (t, sm_mhz, reasons bitmask)
+        self.t_begin = self.t_end = None
+        self.max_mhz = None
+        self._stop = False
+
+    def _nvml_loop(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            t0 = self.t_begin if self.t_begin is not None else -1e300
+            t1 = self.t_end if self.t_end is not None else 1e300
+            inside = [s_ for s_ in self.samples if t0 <= s_[0] <= t1]
+            how = "inside the timed region"
+            if not inside and self.samples:      # region shorter than one polling period
+                mid = 0.5 * (t0 + t1)
+                inside = sorted(self.samples, key=lambda s_: abs(s_[0] - mid))[:3]
+                how = "nearest to the timed region"
+            if inside:
+                bits = 0
+                for s_ in inside:
+                    bits |= s_[2]
+                names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                         "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                         "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+                out = {"sm_mhz": float(np.median([s_[1] for s_ in inside])), "sm_max_mhz": self.max_mhz,
+                       "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(inside),
+                       "source": "NVML polling thread, " + how}
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -106,7 +166,7 @@ class ClockSampler:
                     reasons.add(nm)
         if sm:
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "source": "nvidia-smi -lms 20"}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -230,15 +290,16 @@ def run_ours(args):
     # the last completed iteration (the 100-trial zoom that fails is not an iteration and is not
     # timed) and a fresh run is started from x0 (state allocation and the f/g evaluation at x0 are
     # set-up, as for the first run).  With the default K + W <= 50 this never triggers on cfg 3.
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # polling runs through the warm-up; only the timed window is reported
     run = cg.MinimizerRun(obj, x0, cfg, ls)
     for _ in range(W):
         assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
     ctx.timing(True)
     ctx.timing_read(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.mark_begin()
     launches = 0
     ms, wall_ms, evals, done, restarts, life = 0.0, 0.0, 0, 0, 0, None
     trace_f = None
@@ -272,6 +333,7 @@ def run_ours(args):
             run.info.close()
             run = cg.MinimizerRun(obj, x0, cfg, ls)
             restarts += 1
+    sampler.mark_end()
     barrier()
     timers = ctx.timing_read(reset=True)
     ctx.timing(False)
@@ -405,13 +467,19 @@ def run_batched(args):
         res = cg.minimizeobjective_batched(X0p, cfg, ls, ctx)
     ctx.timing(True)
     ctx.timing_read(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     l0 = ctx.kernel_launches
     torch.cuda.synchronize()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(K):
         res = cg.minimizeobjective_batched(X0p, cfg, ls, ctx)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     kms = ctx.timing_read(reset=True)["batched"][0]
     ctx.timing(False)
     t = torch.tensor([kms, wall], dtype=torch.float64, device="cuda")
@@ -441,7 +509,7 @@ def run_batched(args):
                 "e2e": {"value": round(tot_it * K / wall, 1), "unit": "iterations/s",
                         "h2d_bytes_per_step": 8.0 * nprob * n, "d2h_bytes_per_step": 8.0 * nprob * n + 36.0 * nprob,
                         "includes": "x0 H2D from pinned memory, solve, minimizers + per-problem results D2H"},
-                "gpu_launches": int(ctx.kernel_launches - l0), "clocks": None, "cpu_baseline": None}
+                "gpu_launches": int(ctx.kernel_launches - l0), "clocks": clocks, "cpu_baseline": None}
     return line, ctx
 
 
