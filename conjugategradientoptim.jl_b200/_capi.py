@@ -50,6 +50,7 @@ _SIGS = {
     "cgo_comm_get_unique_id": (C.c_int, [_vp]),
     "cgo_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cgo_ctx_barrier": (C.c_int, [_vp]),
+    "cgo_ctx_peer_memory": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cgo_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "cgo_host_free": (C.c_int, [_vp]),
     "cgo_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(CGO_B, Op::OCC) k_blas1(Op op, int64_t n, RedA
     constexpr int64_t tileq = (int64_t)CGO_B * CGO_U_VEC;
     const int64_t ntiles = (nq + tileq - 1) / tileq;
     const int nact = (int)(ntiles < (int64_t)red.G ? ntiles : (int64_t)red.G);
+    cgo_wait_flags(red, BarAll());
     op.prologue();
     for (int v = blockIdx.x; v < nact; v += gridDim.x) {
         double acc[K];
@@ -205,8 +206,10 @@ struct NormUPlusG {
     }
 };
 
-// xp = x + a u, optionally after u = −g + βu; pack {g·u, u·u, xp·xp}
-template <bool FUSED>
+// xp = x + a u, optionally after u = −g + βu; pack {g·u, u·u, xp·xp}.  PUSH: the first / last
+// `hq` double2 of xp are also stored into the ring neighbours' halos (peer memory, NVLink) —
+// the halo exchange of the sharded CSR objectives, fused into the kernel that produces xp.
+template <bool FUSED, int PUSH>      // PUSH: 0 none, 1 ring halos, 2 whole shard to every rank
 struct AxpyDir {
     static constexpr int TCLASS = CGO_T_AXPY;
     static constexpr int K = 3;
@@ -215,6 +218,10 @@ struct AxpyDir {
     const double2 *x, *g;
     double2 *u, *xp;
     double a, beta;
+    double2 *prev_right, *next_left;     // PUSH 1
+    int64_t hq, nq;                      // PUSH 1: halo and local length in double2
+    void *const *dst_all;                // PUSH 2: nranks destinations (device table)
+    int nranks;
     __device__ __forceinline__ void prologue() {}
     __device__ __forceinline__ In load(int64_t q) const {
         In r;
@@ -234,6 +241,13 @@ struct AxpyDir {
         p.x = in.x.x + a * uu.x;
         p.y = v2 ? in.x.y + a * uu.y : 0.0;
         cgo_st2(xp + q, p);
+        if (PUSH == 1) {
+            if (q < hq) cgo_st2(prev_right + q, p);
+            if (q >= nq - hq) cgo_st2(next_left + (q - (nq - hq)), p);
+        }
+        if (PUSH == 2) {
+            for (int r = 0; r < nranks; ++r) cgo_st2((double2 *)dst_all[r] + q, p);
+        }
         acc[0] = acc[0] + in.g.x * uu.x;
         acc[1] = acc[1] + uu.x * uu.x;
         acc[2] = acc[2] + p.x * p.x;
@@ -261,9 +275,9 @@ struct GradCombine {
     __device__ __forceinline__ void prologue() {}
     __device__ __forceinline__ In load(int64_t i) const {
         In r;
-        r.s = cgo_ld2(q + i);
+        r.s = ld2rw(q + i);          // coherent loads: peers deliver q while this kernel waits for their flags
         for (int p = 1; p < nparts; ++p) {
-            const double2 t = cgo_ld2(q + (int64_t)p * stride2 + i);
+            const double2 t = ld2rw(q + (int64_t)p * stride2 + i);
             r.s.x = r.s.x + t.x;
             r.s.y = r.s.y + t.y;
         }
@@ -467,6 +481,14 @@ extern "C" int cgo_state_destroy(cgo_state *st) {
     if (!st) return 0;
     cudaSetDevice(st->ctx->device);
     cudaStreamSynchronize(st->ctx->stream);
+    if (st->peer_x) {               // collective: the neighbours unmap before the owner frees
+        for (int k = 0; k < 2; ++k) {
+            if (st->xpeers[k].size() != (size_t)st->ctx->nranks) continue;
+            double *mine = (double *)st->xpeers[k][(size_t)st->ctx->rank];
+            for (int i = 0; i < 5; ++i) if (st->base[i] == mine) st->base[i] = nullptr;
+            cgo_peer_free(st->ctx, mine, st->xpeers[k], true);
+        }
+    }
     for (int i = 0; i < 5; ++i) cudaFree(st->base[i]);
     for (auto p : st->S) cudaFree(p);
     for (auto p : st->Y) cudaFree(p);
@@ -486,10 +508,20 @@ extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, in
     // halo must keep 16-byte alignment of the local part
     CGO_CHECK(st->halo % 2 == 0, "halo must be even");
     double **ptrs[5] = {&st->x, &st->g, &st->u, &st->xp, &st->gp};
+    st->peer_x = ctx->nranks > 1 && ctx->peer_ok && st->halo > 0;
     for (int i = 0; i < 5; ++i) {
-        int r = alloc_vec(st, &st->base[i], ptrs[i]);
+        int r;
+        if (st->peer_x && (i == 0 || i == 3)) {      // x and xp: mapped by the ring neighbours
+            void *p = nullptr;
+            r = cgo_peer_alloc(ctx, sizeof(double) * (size_t)(st->n + 2 * st->halo + 4), &p, st->xpeers[i == 0 ? 0 : 1]);
+            st->base[i] = (double *)p;
+            *ptrs[i] = st->base[i] + st->halo;
+        } else {
+            r = alloc_vec(st, &st->base[i], ptrs[i]);
+        }
         if (r) { cgo_state_destroy(st); return r; }
     }
+    st->xp_alloc = 1;
     st->m = lbfgs_m;
     if (lbfgs_m > 0) {
         size_t len = (size_t)(st->n + 4);
@@ -522,6 +554,7 @@ extern "C" int cgo_accept(cgo_state *st) {
     std::swap(st->g, st->gp);
     std::swap(st->base[0], st->base[3]);
     std::swap(st->base[1], st->base[4]);
+    st->xp_alloc ^= 1;
     return 0;
 }
 
@@ -570,27 +603,46 @@ extern "C" int cgo_norm_sq_u_plus_g(cgo_state *st, double *outv) {
     return 0;
 }
 
-int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta) {
+template <bool FUSED, int PUSH>
+static int launch_axpy_dir(cgo_state *st, double a, double beta, const HaloPush *push) {
     // writes {g·u, u·u, xp·xp} to pack slots CGO_P_DIR_GU, CGO_P_DIR_UU, CGO_P_XPXP
-    const RedArgs red = cgo_red_args(st->ctx, CGO_P_DIR_GU);
-    if (fused) {
-        AxpyDir<true> op;
-        op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
-        op.xp = (double2 *)st->xp; op.a = a; op.beta = beta;
-        return launch_blas1(st->ctx, op, st->n, red);
-    }
-    AxpyDir<false> op;
+    cgo_ctx *c = st->ctx;
+    RedArgs red = cgo_red_args(c, CGO_P_DIR_GU);
+    AxpyDir<FUSED, PUSH> op;
     op.x = (const double2 *)st->x; op.g = (const double2 *)st->g; op.u = (double2 *)st->u;
-    op.xp = (double2 *)st->xp; op.a = a; op.beta = 0.0;
-    return launch_blas1(st->ctx, op, st->n, red);
+    op.xp = (double2 *)st->xp; op.a = a; op.beta = FUSED ? beta : 0.0;
+    op.prev_right = op.next_left = nullptr; op.hq = 0; op.nq = st->n / 2;
+    op.dst_all = nullptr; op.nranks = c->nranks;
+    if (PUSH == 1) {
+        op.prev_right = (double2 *)push->prev_right; op.next_left = (double2 *)push->next_left;
+        op.hq = st->halo / 2;
+        red.sig0 = push->sig_prev; red.sig1 = push->sig_next; red.sig_val = push->epoch;
+    }
+    if (PUSH == 2) {
+        op.dst_all = push->dst_all;
+        red.flags_all = c->d_flags_peer; red.sig_all_slot = CGO_F_XPALL; red.nranks = c->nranks; red.me = c->rank;
+        red.sig_val = push->epoch;
+    }
+    return launch_blas1(c, op, st->n, red);
+}
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta, const HaloPush *push) {
+    if (push && push->dst_all)
+        return fused ? launch_axpy_dir<true, 2>(st, a, beta, push) : launch_axpy_dir<false, 2>(st, a, beta, push);
+    if (push) return fused ? launch_axpy_dir<true, 1>(st, a, beta, push) : launch_axpy_dir<false, 1>(st, a, beta, push);
+    return fused ? launch_axpy_dir<true, 0>(st, a, beta, nullptr) : launch_axpy_dir<false, 0>(st, a, beta, nullptr);
 }
 
-int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda) {
+int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda,
+                           unsigned long long wait_epoch) {
     GradCombine op;
     op.q = (const double2 *)q; op.u = (const double2 *)st->u; op.g = (const double2 *)st->g;
     op.w = (const double2 *)st->xp; op.gp = (double2 *)st->gp;
     op.nparts = nparts; op.stride2 = stride / 2; op.invN = invN; op.lambda = lambda;
-    return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx, CGO_P_DPHI));
+    RedArgs red = cgo_red_args(st->ctx, CGO_P_DPHI);
+    if (wait_epoch) {
+        red.wait_all = st->ctx->flags_local + CGO_F_GPART; red.wait_val = wait_epoch; red.nranks = st->ctx->nranks;
+    }
+    return launch_blas1(st->ctx, op, st->n, red);
 }
 
 // ------------------------------------------------------------------ L-BFGS
@@ -622,22 +674,13 @@ extern "C" int cgo_lbfgs_commit_pair(cgo_state *st, int32_t commit, double rho, 
 }
 
 // publish the dot of the kernel that just ran into d_scal[slot] (all ranks, rank order)
-__global__ void k_sum_ranks_to(const double *gathered, int nranks, double *dst) {
-    double s = gathered[0];
-    for (int r = 1; r < nranks; ++r) s = s + gathered[(size_t)r * CGO_PACK_LEN];
-    *dst = s;
-}
 static RedArgs red_to_slot(cgo_ctx *c, int slot) {
     RedArgs r = cgo_red_args(c);
     r.out = (c->nranks > 1) ? c->d_pack : c->d_scal + slot;
     return r;
 }
 static int publish_slot(cgo_ctx *c, int slot) {
-    if (c->nranks > 1) {
-        CGO_TRY(cgo_allgather_bytes(c, c->d_pack, c->d_gather, sizeof(double) * CGO_PACK_LEN));
-        k_sum_ranks_to<<<1, 1, 0, c->stream>>>(c->d_gather, c->nranks, c->d_scal + slot);
-        c->launches++;
-    }
+    if (c->nranks > 1) CGO_TRY(cgo_combine_ranks(c, 1, c->d_scal + slot));
     return 0;
 }
 

@@ -2,9 +2,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.cuh"
+#include "reduce.cuh"
 
 // ------------------------------------------------------------------ error channel
 static thread_local char g_err[1024] = "";
@@ -96,6 +98,9 @@ extern "C" int cgo_ctx_destroy(cgo_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->gather_local) cgo_peer_free(c, c->gather_local, c->gather_peer, false);
+    if (c->flags_local) cgo_peer_free(c, c->flags_local, c->flags_peer, false);   // teardown: no collective
+    cudaFree(c->d_gather_peer); cudaFree(c->d_flags_peer);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)c->comm);
     cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFreeHost(c->h_pack);
     cudaFree(c->d_pack); cudaFree(c->d_gather); cudaFree(c->d_scal);
@@ -157,6 +162,88 @@ extern "C" int cgo_ctx_comm_init(cgo_ctx *c, int nranks, int rank, const void *i
     c->comm = (void *)comm;
     c->nccl = &g_nccl;
     CGO_CUDA(cudaMalloc(&c->d_gather, sizeof(double) * CGO_PACK_LEN * nranks));
+    // peer memory: every rank maps every other rank's flag block (CUDA IPC; one node).  When the
+    // mapping is refused (no P2P route, IPC disabled, CGO_NO_PEER=1) the halo exchanges stay on
+    // NCCL point-to-point transfers.
+    const char *no_peer = getenv("CGO_NO_PEER");
+    void *fl = nullptr;
+    c->peer_ok = true;
+    int rc = (no_peer && no_peer[0] == '1') ? 4 : cgo_peer_alloc(c, sizeof(unsigned long long) * CGO_F_N, &fl, c->flags_peer);
+    c->flags_local = (unsigned long long *)fl;
+    // every rank must take the same path: agree through the communicator
+    double ok = (rc == 0) ? 1.0 : 0.0, *d_ok = c->d_scal + CGO_NSCAL - 2;
+    CGO_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CGO_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclMin, comm, c->stream));
+    CGO_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    c->peer_ok = ok > 0.5;
+    if (c->peer_ok) {
+        CGO_CHECK(nranks <= CGO_MAX_RANKS, "at most %d ranks", CGO_MAX_RANKS);
+        void *gl = nullptr;
+        CGO_TRY(cgo_peer_alloc(c, sizeof(double) * 2 * (size_t)nranks * CGO_PACK_LEN, &gl, c->gather_peer));
+        c->gather_local = (double *)gl;
+        CGO_CUDA(cudaMalloc(&c->d_gather_peer, sizeof(void *) * (size_t)nranks));
+        CGO_CUDA(cudaMalloc(&c->d_flags_peer, sizeof(void *) * (size_t)nranks));
+        CGO_CUDA(cudaMemcpy(c->d_gather_peer, c->gather_peer.data(), sizeof(void *) * (size_t)nranks, cudaMemcpyHostToDevice));
+        CGO_CUDA(cudaMemcpy(c->d_flags_peer, c->flags_peer.data(), sizeof(void *) * (size_t)nranks, cudaMemcpyHostToDevice));
+        CGO_TRY(cgo_ctx_barrier(c));
+    }
+    return 0;
+}
+extern "C" int cgo_ctx_peer_memory(cgo_ctx *c, int *enabled) {
+    CGO_CHECK(c && enabled, "NULL argument");
+    *enabled = (c->nranks > 1 && c->peer_ok) ? 1 : 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------ peer memory (CUDA IPC)
+int cgo_peer_alloc(cgo_ctx *c, size_t bytes, void **local, std::vector<void *> &peers) {
+    const int R = c->nranks;
+    *local = nullptr;
+    peers.assign((size_t)R, nullptr);
+    CGO_CUDA(cudaMalloc(local, bytes));
+    CGO_CUDA(cudaMemsetAsync(*local, 0, bytes, c->stream));
+    peers[(size_t)c->rank] = *local;
+    if (R == 1) return 0;
+    CGO_CHECK(c->peer_ok, "peer memory is not available on this communicator");
+    cudaIpcMemHandle_t mine;
+    CGO_CUDA(cudaIpcGetMemHandle(&mine, *local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    unsigned char *d_h = nullptr;
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    int rc = 0;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&d_h, 64 * (size_t)(R + 1)));
+        CGO_CUDA(cudaMemcpyAsync(d_h + 64 * (size_t)R, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+        CGO_NCCL(g_nccl.AllGather(d_h + 64 * (size_t)R, d_h, 64, ncclInt8, (ncclComm_t)c->comm, c->stream));
+        CGO_CUDA(cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
+        CGO_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    rc = body();
+    cudaFree(d_h);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r) {
+        if (r == c->rank) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&peers[(size_t)r], all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cgo_set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return 1;
+        }
+    }
+    return 0;
+}
+int cgo_peer_free(cgo_ctx *c, void *local, std::vector<void *> &peers, bool collective) {
+    if (!local) return 0;
+    if (c->nranks > 1) {
+        if (collective) cgo_ctx_barrier(c);       // nobody still writes into / reads from the blocks
+        for (int r = 0; r < (int)peers.size(); ++r)
+            if (r != c->rank && peers[(size_t)r]) cudaIpcCloseMemHandle(peers[(size_t)r]);
+        if (collective) cgo_ctx_barrier(c);       // every mapping is closed before the owner frees
+    }
+    peers.clear();
+    cudaFree(local);
     return 0;
 }
 
@@ -310,12 +397,55 @@ __global__ void k_sum_ranks(const double *gathered, int nranks, int K, double *o
     __threadfence_system();
 }
 
-int cgo_finish_pack(cgo_ctx *c, int K, double *out_host) {
-    if (c->nranks > 1) {
-        CGO_NCCL(g_nccl.AllGather(c->d_pack, c->d_gather, CGO_PACK_LEN, ncclFloat64, (ncclComm_t)c->comm, c->stream));
-        k_sum_ranks<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, K, c->d_pack_map);
-        c->launches++;
+// All-gather of the scalar pack over peer memory + rank-ordered sum, one small kernel: thread
+// (r, k) stores my pack entry k into rank r's gather block, thread r then release-stores my
+// flag in rank r's flag block; thread r waits for rank r's flag here, and the first K threads
+// add the R packs in rank order.  Double-buffered by the epoch's parity (a fast rank may already
+// deliver the next pack while a slow one still sums this one).
+__global__ void k_pack_exchange(const double *pack, void *const *gather_peer, void *const *flags_peer,
+                                const double *gather_local, const unsigned long long *flags_local,
+                                int nranks, int me, int K, unsigned long long epoch, double *out) {
+    const int t = threadIdx.x;
+    const size_t buf = (size_t)(epoch & 1ULL) * (size_t)nranks * CGO_PACK_LEN;
+    for (int i = t; i < nranks * CGO_PACK_LEN; i += blockDim.x) {
+        const int r = i / CGO_PACK_LEN, k = i - r * CGO_PACK_LEN;
+        double *dst = (double *)gather_peer[r] + buf + (size_t)me * CGO_PACK_LEN + k;
+        *dst = k < K ? pack[k] : 0.0;
     }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) {
+        cgo_st_release_sys((unsigned long long *)flags_peer[t] + CGO_F_PACK + me, epoch);
+        while (cgo_ld_acquire_sys(flags_local + CGO_F_PACK + t) < epoch) __nanosleep(32);
+    }
+    __syncthreads();
+    if (t < K) {
+        const double *g = gather_local + buf;
+        double s = __ldcv(g + t);
+        for (int r = 1; r < nranks; ++r) s = s + __ldcv(g + (size_t)r * CGO_PACK_LEN + t);
+        out[t] = s;
+    }
+    __threadfence_system();
+}
+// after the kernels of one sequence wrote their sums to d_pack: combine the ranks' packs into
+// `out_dev` (device or mapped host memory) on every rank, in rank order
+int cgo_combine_ranks(cgo_ctx *c, int K, double *out_dev) {
+    if (c->peer_ok) {
+        const unsigned long long e = ++c->pack_epoch;
+        k_pack_exchange<<<1, 128, 0, c->stream>>>(c->d_pack, c->d_gather_peer, c->d_flags_peer, c->gather_local,
+                                                  c->flags_local, c->nranks, c->rank, K, e, out_dev);
+        c->launches++;
+        CGO_CUDA(cudaGetLastError());
+        return 0;
+    }
+    CGO_NCCL(g_nccl.AllGather(c->d_pack, c->d_gather, CGO_PACK_LEN, ncclFloat64, (ncclComm_t)c->comm, c->stream));
+    k_sum_ranks<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, K, out_dev);
+    c->launches++;
+    return 0;
+}
+
+int cgo_finish_pack(cgo_ctx *c, int K, double *out_host) {
+    if (c->nranks > 1) CGO_TRY(cgo_combine_ranks(c, K, c->d_pack_map));
     CGO_CUDA(cudaStreamSynchronize(c->stream));
     if (c->timing) cgo_timer_collect(c);
     for (int k = 0; k < K; ++k) out_host[k] = c->h_pack[k];

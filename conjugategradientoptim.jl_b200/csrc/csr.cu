@@ -218,6 +218,7 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
 
     // ---------------- 256 row lanes
     const BarLanes bar;
+    cgo_wait_flags(red, bar);                 // sharded: the neighbours' halo pushes have landed
     const uint64_t gpol = l2_policy_evict_last();
     uint32_t c = 0, head = 0;                 // chunks consumed, ring offset of the next chunk
     for (int v = blockIdx.x; v < nact; v += gridDim.x) {
@@ -317,18 +318,27 @@ struct EpiStore {                       // y = A x
     __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
     __device__ __forceinline__ void row(int64_t i, double sum, const Pre &, double (&)[K]) const { y[i] = sum; }
 };
-struct EpiResidual {                    // r = A xp − b ; Σ r²
+// r = A xp − b ; Σ r².  PUSH: the first / last `halo` residuals also go straight into the ring
+// neighbours' halos of r (peer memory), where their SpMVᵀ gathers them.
+template <bool PUSH>
+struct EpiResidualT {
     static constexpr int K = 1, NOPS = 1;
     static constexpr bool HAS_INIT = false;
     struct Pre { double b; };
     __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
     const double *b;
     double *r;
+    double *prev_right, *next_left;      // PUSH
+    int64_t halo, nrows;                 // PUSH
     __device__ __forceinline__ const double *operand(int) const { return b; }
     __device__ __forceinline__ Pre load(const double *ops, int t) const { return Pre{ops[t]}; }
     __device__ __forceinline__ void row(int64_t i, double sum, const Pre &p, double (&acc)[K]) const {
         const double rr = sum - p.b;
         r[i] = rr;                      // re-read (gathered) by K_c: keep it cacheable
+        if (PUSH) {
+            if (i < halo) prev_right[i] = rr;
+            if (i >= nrows - halo) next_left[i - (nrows - halo)] = rr;
+        }
         acc[0] = acc[0] + rr * rr;
     }
 };
@@ -385,6 +395,27 @@ struct EpiLogit {
         const double sg = t >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
         c[i] = -y * sg;
         acc[0] = acc[0] + l;
+    }
+};
+
+// Sample-sharded logistic regression over peer memory: row j of Aᵀ_r c_r belongs to the feature
+// shard of rank o; store it straight into rank o's receive block (slice `me`) — the all-to-all
+// fused into the SpMVᵀ epilogue.
+struct EpiPushPart {
+    static constexpr int K = 1, NOPS = 0;
+    static constexpr bool HAS_INIT = false;
+    struct Pre {};
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
+    void *const *recv_all;               // device table: rank o's g_recv + me * stride
+    const int64_t *flo;                  // device copy of the feature shard boundaries, nranks + 1
+    int nranks;
+    __device__ __forceinline__ const double *operand(int) const { return nullptr; }
+    __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
+    __device__ __forceinline__ void row(int64_t j, double sum, const Pre &, double (&)[K]) const {
+        int o = (int)((j * nranks) / flo[nranks]);           // shards are near-uniform: a close first guess
+        while (o > 0 && j < flo[o]) --o;
+        while (o + 1 < nranks && j >= flo[o + 1]) ++o;
+        ((double *)recv_all[o])[j - flo[o]] = sum;
     }
 };
 
@@ -786,12 +817,17 @@ static int build_blocked(cgo_ctx *c, const CsrMat &A, int64_t ncols, CsrBlocked 
     return rc;
 }
 // one pass per column block; the last pass runs the real epilogue
+// (`wait_first`: red's flag wait guards the gathered vector, so the FIRST pass has to honour it)
 template <class Epi>
 static int launch_csr_blocked(cgo_ctx *c, const CsrMat &A, const CsrBlocked &B, const double *xg, const Epi &epi,
-                              double *partial, const RedArgs &red, int tclass) {
+                              double *partial, const RedArgs &red, int tclass, bool wait_first = false) {
     if (B.blk.empty()) return launch_csr(c, A, xg, epi, red, tclass);
     const size_t nb = B.blk.size();
-    const RedArgs scratch = cgo_red_args(c, CGO_PACK_LEN - 1);
+    RedArgs scratch = cgo_red_args(c, CGO_PACK_LEN - 1);
+    if (wait_first) {
+        scratch.wait0 = red.wait0; scratch.wait1 = red.wait1; scratch.wait_all = red.wait_all;
+        scratch.wait_val = red.wait_val; scratch.nranks = red.nranks;
+    }
     for (size_t j = 0; j + 1 < nb; ++j) {
         EpiStore es{partial};
         if (j == 0) CGO_TRY(launch_csr(c, B.blk[j], xg, es, scratch, tclass));
@@ -809,6 +845,8 @@ struct CsrObj : cgo_obj {
     int64_t nrows = 0;                 // local rows of A (residuals / samples)
     double *b = nullptr;               // rhs (LS) or labels (logreg), nrows
     double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
+    std::vector<void *> rpeers;               // peer mappings of r_base (sharded LS with peer memory)
+    bool r_is_peer = false;
     double lambda = 0.0;
     int64_t nsamples = 0;
     // sample-sharded logistic regression (nranks > 1): A holds this rank's samples × all features,
@@ -819,17 +857,76 @@ struct CsrObj : cgo_obj {
     double *g_part = nullptr;          // Aᵀ_r c_r, n_global
     double *g_recv = nullptr;          // nranks × part_stride: every rank's slice of my shard
     int64_t part_stride = 0;
+    // peer-memory variant: xp_full and g_recv are mapped by every rank
+    bool lr_peer = false;
+    std::vector<void *> xpf_peers, grecv_peers;
+    void **d_xpf_dst = nullptr;        // rank r's xp_full + flo[me]
+    void **d_grecv_dst = nullptr;      // rank r's g_recv + me * part_stride
+    int64_t *d_flo = nullptr;
     ~CsrObj() override {
         if (ctx) cudaSetDevice(ctx->device);
         csr_free(A); csr_free(AT);
         Ab.free_all(); ATb.free_all();
+        if (r_is_peer) { cgo_peer_free(ctx, r_base, rpeers, true); r_base = nullptr; }
+        if (lr_peer) {
+            cgo_peer_free(ctx, xp_full, xpf_peers, true); xp_full = nullptr;
+            cgo_peer_free(ctx, g_recv, grecv_peers, true); g_recv = nullptr;
+        }
+        cudaFree(d_xpf_dst); cudaFree(d_grecv_dst); cudaFree(d_flo);
         cudaFree(b); cudaFree(r_base);
         cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
     }
     int alloc_r() {
-        CGO_CUDA(cudaMalloc(&r_base, sizeof(double) * (size_t)(nrows + 2 * halo + 4)));
-        CGO_CUDA(cudaMemsetAsync(r_base, 0, sizeof(double) * (size_t)(nrows + 2 * halo + 4), ctx->stream));
+        const size_t bytes = sizeof(double) * (size_t)(nrows + 2 * halo + 4);
+        if (ctx->nranks > 1 && ctx->peer_ok && halo > 0) {
+            void *p = nullptr;
+            r_is_peer = true;
+            CGO_TRY(cgo_peer_alloc(ctx, bytes, &p, rpeers));
+            r_base = (double *)p;
+        } else {
+            CGO_CUDA(cudaMalloc(&r_base, bytes));
+            CGO_CUDA(cudaMemsetAsync(r_base, 0, bytes, ctx->stream));
+        }
         r = r_base + halo;
+        return 0;
+    }
+    // local length of rank q's shard (the vector shards and the row shards coincide for LS)
+    int64_t shard_len_of(int q) const {
+        int64_t lo, hi;
+        cgo_shard_range(n_global, ctx->nranks, q, 2, &lo, &hi);
+        return hi - lo;
+    }
+    // sharded least squares over peer memory: K_a and K_b push their boundary elements into the
+    // neighbours' halos and hand off with flags; no separate exchange step
+    int eval_trial_ls_peer(cgo_state *st, double a, bool fused, double beta, double *out) {
+        const int R = ctx->nranks, me = ctx->rank, prev = (me + R - 1) % R, next = (me + 1) % R;
+        const unsigned long long e = ++ctx->epoch;
+        unsigned long long *fprev = (unsigned long long *)ctx->flags_peer[(size_t)prev];
+        unsigned long long *fnext = (unsigned long long *)ctx->flags_peer[(size_t)next];
+        const int64_t nprev = shard_len_of(prev);
+        HaloPush hp;
+        double *xp_prev = (double *)st->xpeers[st->xp_alloc][(size_t)prev] + halo;   // origin of prev's xp
+        double *xp_next = (double *)st->xpeers[st->xp_alloc][(size_t)next] + halo;
+        hp.prev_right = xp_prev + nprev;
+        hp.next_left = xp_next - halo;
+        hp.sig_prev = fprev + CGO_F_XP_FROM_NEXT;       // I am prev's next
+        hp.sig_next = fnext + CGO_F_XP_FROM_PREV;
+        hp.epoch = e;
+        CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                          // K_a + halo push
+        EpiResidualT<true> e1;
+        e1.b = b; e1.r = r; e1.halo = halo; e1.nrows = nrows;
+        e1.prev_right = (double *)rpeers[(size_t)prev] + halo + nprev;
+        e1.next_left = (double *)rpeers[(size_t)next];
+        RedArgs rb = cgo_red_args(ctx, CGO_P_PHI);
+        rb.wait0 = ctx->flags_local + CGO_F_XP_FROM_PREV; rb.wait1 = ctx->flags_local + CGO_F_XP_FROM_NEXT; rb.wait_val = e;
+        rb.sig0 = fprev + CGO_F_R_FROM_NEXT; rb.sig1 = fnext + CGO_F_R_FROM_PREV; rb.sig_val = e;
+        CGO_TRY(launch_csr(ctx, A, st->xp, e1, rb, CGO_T_SPMV));                       // K_b + halo push
+        EpiGrad<false> e2{st->gp, st->g, st->u, nullptr, 0.0, 0.0};
+        RedArgs rc = cgo_red_args(ctx, CGO_P_DPHI);
+        rc.wait0 = ctx->flags_local + CGO_F_R_FROM_PREV; rc.wait1 = ctx->flags_local + CGO_F_R_FROM_NEXT; rc.wait_val = e;
+        CGO_TRY(launch_csr(ctx, AT, r, e2, rc, CGO_T_SPMVT));                          // K_c
+        CGO_TRY(cgo_finish_pack(ctx, 12, out));
+        out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
         return 0;
     }
     // fill v[−halo, 0) and v[nloc, nloc + halo) from the ring neighbours
@@ -838,6 +935,30 @@ struct CsrObj : cgo_obj {
         return cgo_sendrecv_ring(ctx, v, v + nloc, v + nloc - halo, v - halo, halo);
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);
+        if (lr_sharded && lr_peer) {
+            // the same data flow with both exchanges fused into the producing kernels: K_a stores
+            // its shard of xp into every rank's all-gathered copy, the last SpMVᵀ pass stores each
+            // row into its owner's receive block; flags hand the data to the consuming kernels
+            const unsigned long long e = ++ctx->epoch;
+            HaloPush hp;
+            hp.dst_all = d_xpf_dst; hp.epoch = e;
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                     // K_a + all-gather
+            EpiLogit e1{b, r};
+            RedArgs rb = cgo_red_args(ctx, CGO_P_PHI);
+            rb.wait_all = ctx->flags_local + CGO_F_XPALL; rb.wait_val = e; rb.nranks = ctx->nranks;
+            CGO_TRY(launch_csr_blocked(ctx, A, Ab, xp_full, e1, r, rb, CGO_T_SPMV, /*wait_first=*/true));   // K_b
+            EpiPushPart e2;
+            e2.recv_all = d_grecv_dst; e2.flo = d_flo; e2.nranks = ctx->nranks;
+            RedArgs rc = cgo_red_args(ctx, CGO_PACK_LEN - 1);
+            rc.flags_all = ctx->d_flags_peer; rc.sig_all_slot = CGO_F_GPART; rc.nranks = ctx->nranks; rc.me = ctx->rank;
+            rc.sig_val = e;
+            CGO_TRY(launch_csr_blocked(ctx, AT, ATb, r, e2, g_part, rc, CGO_T_SPMVT));             // K_c + all-to-all
+            CGO_TRY(cgo_blas1_grad_combine(st, g_recv, ctx->nranks, part_stride, 1.0 / (double)nsamples, lambda, e));
+            CGO_TRY(cgo_finish_pack(ctx, 12, out));
+            out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
+            return 0;
+        }
         CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                               // K_a
         if (lr_sharded) {
             // all-gather xp → margins of my samples → partial gradient over ALL features →
@@ -862,7 +983,8 @@ struct CsrObj : cgo_obj {
             CGO_TRY(cgo_finish_pack(ctx, 12, out));
             out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
         } else {
-            EpiResidual e1{b, r};
+            EpiResidualT<false> e1;
+            e1.b = b; e1.r = r; e1.prev_right = e1.next_left = nullptr; e1.halo = 0; e1.nrows = nrows;
             CGO_TRY(launch_csr(ctx, A, st->xp, e1, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));   // K_b
             CGO_TRY(exchange(r, nrows));
             EpiGrad<false> e2{st->gp, st->g, st->u, nullptr, 0.0, 0.0};
@@ -1036,11 +1158,32 @@ extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t 
             o->have_unblocked = false;
         }
         if (o->lr_sharded) {
-            CGO_CUDA(cudaMalloc(&o->xp_full, sizeof(double) * (size_t)(d + CSR_PAD)));
-            CGO_CUDA(cudaMalloc(&o->g_part, sizeof(double) * (size_t)(d + CSR_PAD)));
-            CGO_CUDA(cudaMalloc(&o->g_recv, sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD)));
-            CGO_CUDA(cudaMemsetAsync(o->xp_full, 0, sizeof(double) * (size_t)(d + CSR_PAD), ctx->stream));
-            CGO_CUDA(cudaMemsetAsync(o->g_recv, 0, sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD), ctx->stream));
+            const size_t xb = sizeof(double) * (size_t)(d + CSR_PAD), gb = sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD);
+            CGO_CUDA(cudaMalloc(&o->g_part, xb));
+            if (ctx->peer_ok) {
+                void *p = nullptr;
+                o->lr_peer = true;
+                CGO_TRY(cgo_peer_alloc(ctx, xb, &p, o->xpf_peers));
+                o->xp_full = (double *)p;
+                CGO_TRY(cgo_peer_alloc(ctx, gb, &p, o->grecv_peers));
+                o->g_recv = (double *)p;
+                std::vector<void *> xd((size_t)R), gd((size_t)R);
+                for (int r = 0; r < R; ++r) {
+                    xd[(size_t)r] = (double *)o->xpf_peers[(size_t)r] + o->flo[(size_t)ctx->rank];
+                    gd[(size_t)r] = (double *)o->grecv_peers[(size_t)r] + (size_t)ctx->rank * o->part_stride;
+                }
+                CGO_CUDA(cudaMalloc(&o->d_xpf_dst, sizeof(void *) * (size_t)R));
+                CGO_CUDA(cudaMalloc(&o->d_grecv_dst, sizeof(void *) * (size_t)R));
+                CGO_CUDA(cudaMalloc(&o->d_flo, sizeof(int64_t) * (size_t)(R + 1)));
+                CGO_CUDA(cudaMemcpy(o->d_xpf_dst, xd.data(), sizeof(void *) * (size_t)R, cudaMemcpyHostToDevice));
+                CGO_CUDA(cudaMemcpy(o->d_grecv_dst, gd.data(), sizeof(void *) * (size_t)R, cudaMemcpyHostToDevice));
+                CGO_CUDA(cudaMemcpy(o->d_flo, o->flo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice));
+            } else {
+                CGO_CUDA(cudaMalloc(&o->xp_full, xb));
+                CGO_CUDA(cudaMalloc(&o->g_recv, gb));
+                CGO_CUDA(cudaMemsetAsync(o->xp_full, 0, xb, ctx->stream));
+                CGO_CUDA(cudaMemsetAsync(o->g_recv, 0, gb, ctx->stream));
+            }
             CGO_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         return 0;

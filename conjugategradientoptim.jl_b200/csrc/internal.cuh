@@ -43,6 +43,19 @@ struct RedArgs {
     unsigned int *ticket;   // arrival counter, self-resetting
     double *out;            // K results: mapped pinned host memory (1 rank) or device (R ranks)
     int G;                  // virtual CTAs of the canonical order
+    // cross-GPU hand-off over peer memory (halo pushes fused into the producing kernel): the
+    // last CTA release-stores sig_val to sig0/sig1 (flags in the neighbours' memory) once every
+    // CTA's peer stores are fenced; a consuming kernel spins until its local wait0/wait1 reach
+    // wait_val before it touches its halos.  nullptr = not used.
+    unsigned long long *sig0 = nullptr, *sig1 = nullptr;
+    const unsigned long long *wait0 = nullptr, *wait1 = nullptr;
+    unsigned long long sig_val = 0, wait_val = 0;
+    // all-ranks variant (sample-sharded logistic regression): the last CTA release-stores sig_val
+    // to slot sig_all_slot + me of EVERY rank's flag block (flags_all[r], device table); a consumer
+    // waits until its local slots wait_all[0 .. nranks) reach wait_val.
+    void *const *flags_all = nullptr;
+    const unsigned long long *wait_all = nullptr;
+    int sig_all_slot = -1, nranks = 1, me = 0;
 };
 
 // ------------------------------------------------------------------ context
@@ -77,7 +90,31 @@ struct cgo_ctx {
     int nranks = 1, rank = 0;
     void *comm = nullptr;            // ncclComm_t
     NcclApi *nccl = nullptr;
+    // peer memory (CUDA IPC between the ranks of one node): flags[r] is rank r's flag block
+    bool peer_ok = false;
+    unsigned long long *flags_local = nullptr;
+    std::vector<void *> flags_peer;  // nranks entries ([rank] = flags_local)
+    unsigned long long epoch = 0;    // advances in lockstep on every rank
+    // scalar-pack exchange over peer memory: gather_peer[r] is rank r's [2][nranks][CGO_PACK_LEN]
+    // block (double-buffered by the parity of pack_epoch)
+    double *gather_local = nullptr;
+    std::vector<void *> gather_peer;
+    void **d_gather_peer = nullptr, **d_flags_peer = nullptr;   // device copies of the pointer tables
+    unsigned long long pack_epoch = 0;
 };
+// flag slots of a rank's block
+// (CGO_F_PACK + r: rank r's scalar pack of the current exchange has landed in my gather block)
+constexpr int CGO_MAX_RANKS = 64;
+// (CGO_F_XPALL + r: rank r's shard of xp has landed in my all-gathered copy; CGO_F_GPART + r: rank r's
+// partial-gradient slice of my feature shard has landed)
+enum { CGO_F_XP_FROM_PREV = 0, CGO_F_XP_FROM_NEXT = 1, CGO_F_R_FROM_PREV = 2, CGO_F_R_FROM_NEXT = 3, CGO_F_PACK = 8,
+       CGO_F_XPALL = 8 + CGO_MAX_RANKS, CGO_F_GPART = 8 + 2 * CGO_MAX_RANKS, CGO_F_N = 8 + 3 * CGO_MAX_RANKS };
+// allocate `bytes` of device memory on every rank (collective) and map every peer's block:
+// peers[r] is rank r's block in this process's address space (peers[rank] == *local).
+int cgo_peer_alloc(cgo_ctx *ctx, size_t bytes, void **local, std::vector<void *> &peers);
+// collective: barrier before the peers unmap and before the owner frees (all ranks call it at the
+// same point of the host program); non-collective only at process teardown
+int cgo_peer_free(cgo_ctx *ctx, void *local, std::vector<void *> &peers, bool collective);
 constexpr int CGO_GMAX = 8192;
 constexpr int CGO_NSCAL = 256;     // device scalar slots (L-BFGS dots), last one reserved
 constexpr int CGO_LBFGS_MAX_M = 64;
@@ -90,6 +127,7 @@ void cgo_timer_begin(cgo_ctx *ctx, int cls);   // records an event on the ctx st
 void cgo_timer_end(cgo_ctx *ctx);
 void cgo_timer_collect(cgo_ctx *ctx);          // after a stream sync: fold pending timers
 int cgo_finish_pack(cgo_ctx *ctx, int K, double *out_host);
+int cgo_combine_ranks(cgo_ctx *ctx, int K, double *out_dev);   // multi-rank: Σ_r d_pack[0..K) in rank order → out_dev
 int cgo_allgather_bytes(cgo_ctx *ctx, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
 int cgo_sendrecv_ring(cgo_ctx *ctx, const double *send_to_prev, double *recv_from_next,
                       const double *send_to_next, double *recv_from_prev, int64_t count);
@@ -118,6 +156,11 @@ struct cgo_state {
     int64_t halo = 0;
     double *base[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // allocations
     double *x = nullptr, *g = nullptr, *u = nullptr, *xp = nullptr, *gp = nullptr;  // base + halo
+    // sharded CSR objectives with peer memory: the two x / xp allocations are mapped by the ring
+    // neighbours, which push their boundary elements of xp straight into this rank's halos
+    bool peer_x = false;
+    std::vector<void *> xpeers[2];   // per allocation (0: base[0]'s, 1: base[3]'s at creation)
+    int xp_alloc = 1;                // which of the two allocations is xp right now (flips on accept)
     // L-BFGS history
     int m = 0, count = 0, head = 0, staged = -1;
     std::vector<double *> S, Y;
@@ -129,10 +172,23 @@ struct cgo_state {
 // BLAS-1 kernels shared by objectives (blas1.cu)
 // xp = x + a u (optionally after u = −g + βu); {g·u, u·u, xp·xp} land in pack slots
 // CGO_P_DIR_GU, CGO_P_DIR_UU, CGO_P_XPXP
-int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta);
+// `push`: also store the first / last `halo` elements of xp into the ring neighbours' halos
+// (peer memory) and signal their flags with `epoch` when the kernel's stores are fenced
+struct HaloPush {
+    double *prev_right = nullptr;    // previous rank's xp + its n (its right halo)
+    double *next_left = nullptr;     // next rank's xp − halo (its left halo)
+    unsigned long long *sig_prev = nullptr, *sig_next = nullptr;
+    unsigned long long epoch = 0;
+    // all-gather variant: my whole shard goes to dst_all[r] (rank r's all-gathered xp at my offset;
+    // device table of nranks pointers), then flag CGO_F_XPALL + me of every rank
+    void *const *dst_all = nullptr;
+};
+int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, const HaloPush *push = nullptr);
 // sample-sharded logistic regression: g⁺ = (Σ_r q[r·stride + i]) / N + λ xp, partial gradients
 // added in rank order, fused with the dot pack of EpiGrad (slots CGO_P_DPHI .. CGO_P_UU)
-int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda);
+// wait_epoch != 0: spin until every rank's CGO_F_GPART flag reached it before reading q
+int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda,
+                           unsigned long long wait_epoch = 0);
 
 // ------------------------------------------------------------------ CSR (csr.cu)
 struct CsrMat {

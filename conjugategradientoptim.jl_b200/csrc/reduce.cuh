@@ -15,6 +15,15 @@ struct BarLanes {
     __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, %0;" ::"n"(CGO_B) : "memory"); }
 };
 
+__device__ __forceinline__ void cgo_st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long cgo_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Combine the CGO_B lanes of a CTA.  Result valid in thread 0 (acc[] of thread 0).
 template <int K, class Bar = BarAll>
 __device__ __forceinline__ void cgo_cta_combine(double (&acc)[K], double *sm /* K*CGO_NW */, Bar bar = Bar()) {
@@ -53,7 +62,8 @@ __device__ __forceinline__ void cgo_publish(const RedArgs &red, int vcta, const 
 template <int K, class Bar = BarAll>
 __device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, double *sm, Bar bar = Bar()) {
     __shared__ bool is_last;
-    __threadfence();
+    if (red.sig0 != nullptr || red.flags_all != nullptr) __threadfence_system();   // this CTA's peer-memory stores
+    else __threadfence();
     bar();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(red.ticket, 1u);
@@ -75,7 +85,28 @@ __device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, do
         for (int k = 0; k < K; ++k) red.out[k] = acc[k];
         *red.ticket = 0u;
         __threadfence_system();
+        if (red.sig0 != nullptr) {      // every CTA fenced its peer stores before its ticket
+            cgo_st_release_sys(red.sig0, red.sig_val);
+            if (red.sig1 != nullptr) cgo_st_release_sys(red.sig1, red.sig_val);
+        }
+        if (red.flags_all != nullptr)
+            for (int r = 0; r < red.nranks; ++r)
+                cgo_st_release_sys((unsigned long long *)red.flags_all[r] + red.sig_all_slot + red.me, red.sig_val);
     }
+}
+
+// consumer side of the hand-off: thread 0 spins on the local flags, `bar` releases the others
+template <class Bar>
+__device__ __forceinline__ void cgo_wait_flags(const RedArgs &red, Bar bar) {
+    if (red.wait0 == nullptr && red.wait_all == nullptr) return;
+    if (threadIdx.x == 0 && red.wait0 != nullptr) {
+        while (cgo_ld_acquire_sys(red.wait0) < red.wait_val) __nanosleep(64);
+        if (red.wait1 != nullptr)
+            while (cgo_ld_acquire_sys(red.wait1) < red.wait_val) __nanosleep(64);
+    }
+    if (red.wait_all != nullptr && (int)threadIdx.x < red.nranks)
+        while (cgo_ld_acquire_sys(red.wait_all + threadIdx.x) < red.wait_val) __nanosleep(64);
+    bar();
 }
 
 // 128-bit streaming loads / stores (inputs are read once per kernel: keep them out of L1)

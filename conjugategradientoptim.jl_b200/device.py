@@ -94,6 +94,13 @@ class Context:
     def barrier(self):
         check(lib().cgo_ctx_barrier(self.h))
 
+    @property
+    def peer_memory(self) -> bool:
+        """True when halo exchanges run as peer-memory stores fused into the kernels (CUDA IPC)."""
+        v = C.c_int()
+        check(lib().cgo_ctx_peer_memory(self.h, C.byref(v)))
+        return bool(v.value)
+
     def close(self):
         if self.h:
             lib().cgo_ctx_destroy(self.h)

@@ -99,6 +99,10 @@ int cgo_ctx_timing_read(cgo_ctx *ctx, double ms[8], int64_t counts[8], int reset
 int cgo_comm_get_unique_id(void *id128);
 int cgo_ctx_comm_init(cgo_ctx *ctx, int nranks, int rank, const void *id128);
 int cgo_ctx_barrier(cgo_ctx *ctx);
+/* 1 when the ranks mapped each other's device memory (CUDA IPC over NVLink / NVSwitch): halo
+ * exchanges are then stores fused into the producing kernels plus a flag hand-off, instead of
+ * NCCL point-to-point transfers.  Environment CGO_NO_PEER=1 forces the NCCL path. */
+int cgo_ctx_peer_memory(cgo_ctx *ctx, int *enabled);
 /* page-locked host memory (Results.minimizer / Results.gradient land in it at PCIe speed; x_initial
  * may live in it too).  Plain pageable pointers are accepted everywhere, just slower. */
 int cgo_host_alloc(size_t bytes, void **out);

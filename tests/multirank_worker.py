@@ -27,6 +27,8 @@ def main():
     ctx.comm_init_torch()
     O.set_cgo_order(296, world)
     fails = []
+    if rank == 0:
+        print(f"PEER_MEMORY={int(ctx.peer_memory)}", flush=True)
 
     def check(name, obj, x0_full, ora_obj, flavour, max_iters):
         ocfg, cfg, ls = make_pair(flavour, max_iters=max_iters)
