@@ -580,6 +580,11 @@ def main():
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+        # peer-mapped device memory and two NCCL communicators are still open: leave their
+        # teardown to process exit instead of the interpreter's unordered finalisers
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

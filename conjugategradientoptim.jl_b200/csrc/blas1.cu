@@ -513,7 +513,9 @@ extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, in
         int r;
         if (st->peer_x && (i == 0 || i == 3)) {      // x and xp: mapped by the ring neighbours
             void *p = nullptr;
-            r = cgo_peer_alloc(ctx, sizeof(double) * (size_t)(st->n + 2 * st->halo + 4), &p, st->xpeers[i == 0 ? 0 : 1]);
+            // same size on every rank: the ranks pool and reuse these blocks in lockstep
+            const int64_t len = (obj->n_alloc > st->n ? obj->n_alloc : st->n) + 2 * st->halo + 4;
+            r = cgo_peer_alloc(ctx, sizeof(double) * (size_t)len, &p, st->xpeers[i == 0 ? 0 : 1]);
             st->base[i] = (double *)p;
             *ptrs[i] = st->base[i] + st->halo;
         } else {

@@ -200,11 +200,22 @@ extern "C" int cgo_ctx_peer_memory(cgo_ctx *c, int *enabled) {
 int cgo_peer_alloc(cgo_ctx *c, size_t bytes, void **local, std::vector<void *> &peers) {
     const int R = c->nranks;
     *local = nullptr;
+    // a block of this size released earlier (every rank pools in lockstep): mapping a peer's
+    // allocation costs milliseconds, so the state vectors of successive runs reuse their blocks
+    auto it = c->peer_pool.find(bytes);
+    if (it != c->peer_pool.end() && !it->second.empty()) {
+        peers = it->second.back();
+        it->second.pop_back();
+        c->peer_pool_bytes -= bytes;
+        *local = peers[(size_t)c->rank];
+        CGO_CUDA(cudaMemsetAsync(*local, 0, bytes, c->stream));
+        return cgo_ctx_barrier(c);       // no neighbour writes into the block before it is cleared
+    }
     peers.assign((size_t)R, nullptr);
     CGO_CUDA(cudaMalloc(local, bytes));
     CGO_CUDA(cudaMemsetAsync(*local, 0, bytes, c->stream));
     peers[(size_t)c->rank] = *local;
-    if (R == 1) return 0;
+    if (R == 1) { c->peer_bytes[*local] = bytes; return 0; }
     CGO_CHECK(c->peer_ok, "peer memory is not available on this communicator");
     cudaIpcMemHandle_t mine;
     CGO_CUDA(cudaIpcGetMemHandle(&mine, *local));
@@ -232,18 +243,42 @@ int cgo_peer_alloc(cgo_ctx *c, size_t bytes, void **local, std::vector<void *> &
             return 1;
         }
     }
+    c->peer_bytes[*local] = bytes;
     return 0;
 }
 int cgo_peer_free(cgo_ctx *c, void *local, std::vector<void *> &peers, bool collective) {
     if (!local) return 0;
-    if (c->nranks > 1) {
-        if (collective) cgo_ctx_barrier(c);       // nobody still writes into / reads from the blocks
-        for (int r = 0; r < (int)peers.size(); ++r)
+    if (c->nranks > 1 && collective && peers.size() == (size_t)c->nranks) {
+        // keep the block and its mappings for the next allocation of this size; the barrier makes
+        // sure no rank still reads or writes it on behalf of the old owner
+        size_t bytes = 0;
+        auto f = c->peer_bytes.find(local);
+        if (f != c->peer_bytes.end()) bytes = f->second;
+        if (bytes && c->peer_pool_bytes + bytes <= ((size_t)16 << 30)) {
+            cgo_ctx_barrier(c);
+            c->peer_pool[bytes].push_back(peers);
+            c->peer_pool_bytes += bytes;
+            peers.clear();
+            return 0;
+        }
+        // pool full: unmap on every rank, then the owner frees
+        cgo_ctx_barrier(c);
+        for (int r = 0; r < c->nranks; ++r)
             if (r != c->rank && peers[(size_t)r]) cudaIpcCloseMemHandle(peers[(size_t)r]);
-        if (collective) cgo_ctx_barrier(c);       // every mapping is closed before the owner frees
+        cgo_ctx_barrier(c);
+        c->peer_bytes.erase(local);
+        cudaFree(local);
+        peers.clear();
+        return 0;
     }
+    if (c->nranks == 1 && collective) {
+        c->peer_bytes.erase(local);
+        cudaFree(local);
+        peers.clear();
+        return 0;
+    }
+    // teardown (or an incomplete mapping): mappings and blocks die with the process
     peers.clear();
-    cudaFree(local);
     return 0;
 }
 

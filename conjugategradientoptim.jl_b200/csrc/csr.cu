@@ -877,8 +877,9 @@ struct CsrObj : cgo_obj {
         cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
     }
     int alloc_r() {
-        const size_t bytes = sizeof(double) * (size_t)(nrows + 2 * halo + 4);
+        size_t bytes = sizeof(double) * (size_t)(nrows + 2 * halo + 4);
         if (ctx->nranks > 1 && ctx->peer_ok && halo > 0) {
+            bytes = sizeof(double) * (size_t)((n_alloc > nrows ? n_alloc : nrows) + 2 * halo + 4);   // rank-independent
             void *p = nullptr;
             r_is_peer = true;
             CGO_TRY(cgo_peer_alloc(ctx, bytes, &p, rpeers));
@@ -1027,6 +1028,11 @@ extern "C" int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n, int32
     int64_t lo, hi;
     CGO_TRY(cgo_shard_range(n, ctx->nranks, ctx->rank, 2, &lo, &hi));
     o->offset = lo; o->n_local = hi - lo; o->nrows = hi - lo;
+    for (int q = 0; q < ctx->nranks; ++q) {
+        int64_t a, b;
+        CGO_TRY(cgo_shard_range(n, ctx->nranks, q, 2, &a, &b));
+        if (b - a > o->n_alloc) o->n_alloc = b - a;
+    }
     const bool multi = ctx->nranks > 1;
     o->halo = multi ? W : 0;
     if (multi) {

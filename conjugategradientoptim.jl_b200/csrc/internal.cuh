@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -101,6 +102,9 @@ struct cgo_ctx {
     std::vector<void *> gather_peer;
     void **d_gather_peer = nullptr, **d_flags_peer = nullptr;   // device copies of the pointer tables
     unsigned long long pack_epoch = 0;
+    std::map<size_t, std::vector<std::vector<void *>>> peer_pool;   // released blocks by size
+    std::map<void *, size_t> peer_bytes;                            // size of every live block
+    size_t peer_pool_bytes = 0;
 };
 // flag slots of a rank's block
 // (CGO_F_PACK + r: rank r's scalar pack of the current exchange has landed in my gather block)
@@ -140,6 +144,7 @@ struct cgo_obj {
     cgo_ctx *ctx = nullptr;
     int64_t n_global = 0, n_local = 0, offset = 0;
     int64_t halo = 0;                 // elements of padding each side of every state vector
+    int64_t n_alloc = 0;              // rank-independent allocation length of peer-mapped vectors (0: n_local)
     virtual ~cgo_obj() {}
     // xp = x + a u (optionally u = −g + β u first), g⁺ = ∇f(xp), fills the device pack and
     // finishes it into out_host.
