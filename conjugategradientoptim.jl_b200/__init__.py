@@ -19,5 +19,5 @@ from .engine import MinimizerRun, minimizeobjective, minimizeobjectivererun  # n
 from .engine.optim import linesearch_  # noqa: F401
 from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceVector,  # noqa: F401
                      LogRegGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,
-                     dot, shard_range, BatchedResults, minimizeobjective_batched)
+                     dot, shard_range, BatchedResults, minimizeobjective_batched, batched_lanes)
 from .device import DeviceLineSearchContainer as LineSearchContainer  # noqa: F401

@@ -26,9 +26,11 @@ class CgoError(RuntimeError):
 
 class BatchedConfig(C.Structure):
     _fields_ = [
-        ("eps", C.c_double), ("max_iters", C.c_int64), ("flavour", C.c_int32), ("_pad", C.c_int32),
+        ("eps", C.c_double), ("max_iters", C.c_int64), ("flavour", C.c_int32), ("linesearch", C.c_int32),
         ("mu", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("growth", C.c_double),
         ("ls_max_iters", C.c_int64), ("zoom_max_iters", C.c_int64),
+        ("delta1", C.c_double), ("max_step_size", C.c_double), ("discount", C.c_double),
+        ("feas_max_iters", C.c_int64),
     ]
 
 
@@ -80,6 +82,7 @@ _SIGS = {
     "cgo_lbfgs_update_dir": (C.c_int, [_vp, _dp]),
     "cgo_download": (C.c_int, [_vp, _dp, _dp]),
     "cgo_download_vector": (C.c_int, [_vp, C.c_int32, _dp]),
+    "cgo_batched_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cgo_batched_minimize_rosenbrock": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp, C.POINTER(BatchedConfig), _dp, _vp, _vp, _vp, _dp, _dp]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGS)

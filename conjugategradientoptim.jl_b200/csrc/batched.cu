@@ -1,76 +1,90 @@
 // batched.cu — many independent small problems, the whole solver on the device
 // (BASELINE.json configs[4]; SURVEY.md §8 cfg 5).
 //
-// One CTA of 256 lanes per problem.  The host cannot drive hundreds of thousands of divergent
-// line-search state machines, so this file restates on the device, scalar for scalar:
+// One CTA per problem.  The host cannot drive hundreds of thousands of divergent line-search
+// state machines, so this file restates on the device, scalar for scalar:
 //   minimizeobjective          src/engine/optim.jl:6-171
 //   linesearch! / zoom!        src/linesearch/nocedal.jl:33-209   (StrongWolfeBisection)
+//   linesearch!, findfeasiblestepsize!, evalwolfeconditions ×2   src/linesearch/wolfe.jl:13-294
+//   linesearch!, geometricsearch!, evalbacktrackcondition        src/linesearch/geometric.jl:22-186
 //   getβ                       src/cg_flavours.jl:51-79 (YuanWangSheng), :87-108 (HagerZhang),
 //                              :133-151 (SallehAlhawarat), :157-170 (LiuStorrey)
 //   updatedir!, initializeLineSearchContainer!   src/cg_flavours.jl:2-35
 //   evalϕdϕ!                   src/cg_utils.jl:3-22, objective = extended Rosenbrock
 // Every lane runs the same scalar state machine on identical reduced scalars (uniform control
-// flow, no divergence inside a problem).  Lane t owns the elements {2q, 2q+1 : q = t + 256 j},
-// i.e. exactly the canonical-order mapping (V = 2, U = 4, one tile) of include/cgoptim.h, so the
-// five n-vectors x, g, u, xp, g⁺ live in REGISTERS and each dot product is the canonical
-// butterfly + warp-ordered sum: results are bit-identical to the oracle run problem by problem
-// (ORC_SUM_CGO, ORC_BETA_FUSED) and to the single-problem device path.  No HBM traffic between
-// reading x0 and writing the result: the roofline that binds is on-chip latency, not HBM.
+// flow, no divergence inside a problem).  The five n-vectors x, g, u, xp, g⁺ live in REGISTERS
+// (up to 8 element pairs per lane); the CTA is as small as that allows — ONE warp for n <= 512 —
+// so a dot product is the lane's sequential sum followed by one five-step shuffle butterfly: no
+// shared memory and no barrier on the BASELINE configuration.  The reduction order is the
+// canonical order of include/cgoptim.h with B = 32·nwarp lanes and one tile; the oracle
+// reproduces it (orc_set_cgo_lanes), so every problem is compared bit for bit.  No HBM traffic
+// between reading x0 and writing the result: the roofline that binds is the FP64 pipe, not HBM.
 #include <math.h>
 
 #include "internal.cuh"
 
 namespace {
 
-constexpr int BT = CGO_B;              // lanes per problem
-constexpr int NW = CGO_NW;
-
 struct Pack9 { double v[9]; };
-
-// canonical CTA combine, result broadcast to every lane.  The warp-ordered final sums are done by
-// K lanes of warp 0 only (FP64 issue slots are the scarce resource of this kernel: having all 256
-// lanes repeat the 8-term sums costs 40 % more FP64 instructions than the objective itself).
-template <int K>
-__device__ __forceinline__ void cta_allreduce(double (&acc)[K], double *scratch /* K * NW + 2 * K */, int &phase) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sm = scratch;
-    double *res = scratch + 9 * NW + phase * 9;      // double-buffered results: no third barrier
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) sm[k * NW + warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {
-        const int k = threadIdx.x;
-        double s = sm[k * NW];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) s = s + sm[k * NW + w];
-        res[k] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = res[k];
-    phase ^= 1;
-}
 
 __device__ __forceinline__ double jl_max(double a, double b) {     // Julia max: NaN-propagating
     if (a != a) return a;
     if (b != b) return b;
     return a > b ? a : b;
 }
+__device__ __forceinline__ double jl_min(double a, double b) {     // Julia min: NaN-propagating
+    if (a != a) return a;
+    if (b != b) return b;
+    return a < b ? a : b;
+}
 
-template <int NPT>
+// One problem = one CTA of BT = 32·NWARP lanes; lane t owns the element pairs {q = t + BT·j,
+// j < NPT} and adds its terms in that order; lanes combine by the xor-butterfly, warps in warp
+// order: the canonical order of include/cgoptim.h with B = BT lanes and a single tile.  The
+// launcher picks the fewest warps that keep NPT <= 8, so that n <= 512 (the BASELINE config)
+// runs on ONE warp: every reduction is five shuffles, no shared memory, no barrier.
+template <int NPT, int NWARP>
 struct Problem {
+    static constexpr int BT = 32 * NWARP;
     double2 x[NPT], g[NPT], u[NPT], xp[NPT], gp[NPT];
     int n;                              // problem dimension (even)
-    double *scratch;
+    double *scratch;                    // NWARP > 1: 9·NWARP + 2·9 doubles of shared memory
     int phase;
     int64_t evals;
 
-    __device__ __forceinline__ bool owns(int j) const { return 2 * (threadIdx.x + j * BT) < n; }
+    __device__ __forceinline__ bool owns(int j) const { return 2 * ((int)threadIdx.x + j * BT) < n; }
+
+    // canonical CTA combine, result in every lane
+    template <int K>
+    __device__ __forceinline__ void allreduce(double (&acc)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+            acc[k] = v;
+        }
+        if (NWARP == 1) return;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double *sm = scratch;
+        double *res = scratch + 9 * NWARP + phase * 9;   // double-buffered results: no third barrier
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) sm[k * NWARP + warp] = acc[k];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < K) {
+            const int k = threadIdx.x;
+            double t = sm[k * NWARP];
+#pragma unroll
+            for (int w = 1; w < NWARP; ++w) t = t + sm[k * NWARP + w];
+            res[k] = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = res[k];
+        phase ^= 1;
+    }
 
     // f, g at x (optim.jl:25): returns f and ‖g‖²
     __device__ __forceinline__ void eval_initial(double &f, double &gg) {
@@ -87,23 +101,39 @@ struct Problem {
                 acc[1] = acc[1] + g[j].y * g[j].y;
             }
         }
-        cta_allreduce<2>(acc, scratch, phase);
+        allreduce<2>(acc);
         f = acc[0]; gg = acc[1];
         evals++;
     }
-    // u = −g + βu (reset: u = −g); returns g·u  (cg_flavours.jl:10-12, :28; nocedal.jl:56)
-    __device__ __forceinline__ double update_dir(double beta, bool reset) {
-        double acc[1] = {0.0};
+    // u = −g + βu (reset: u = −g); g·u and u·u  (cg_flavours.jl:10-12, :28; nocedal.jl:56; wolfe.jl:240)
+    __device__ __forceinline__ void update_dir(double beta, bool reset, double &gu, double &uu) {
+        double acc[2] = {0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < NPT; ++j) {
             if (owns(j)) {
                 if (reset) { u[j].x = -g[j].x; u[j].y = -g[j].y; }
                 else { u[j].x = -g[j].x + beta * u[j].x; u[j].y = -g[j].y + beta * u[j].y; }
                 acc[0] = acc[0] + g[j].x * u[j].x;
+                acc[1] = acc[1] + u[j].x * u[j].x;
                 acc[0] = acc[0] + g[j].y * u[j].y;
+                acc[1] = acc[1] + u[j].y * u[j].y;
             }
         }
-        cta_allreduce<1>(acc, scratch, phase);
+        allreduce<2>(acc);
+        gu = acc[0]; uu = acc[1];
+    }
+    // ‖u + df_x‖² (wolfe.jl:123)
+    __device__ __forceinline__ double norm_sq_u_plus_g() {
+        double acc[1] = {0.0};
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (owns(j)) {
+                const double t1 = u[j].x + g[j].x, t2 = u[j].y + g[j].y;
+                acc[0] = acc[0] + t1 * t1;
+                acc[0] = acc[0] + t2 * t2;
+            }
+        }
+        allreduce<1>(acc);
         return acc[0];
     }
     // evalϕdϕ! (cg_utils.jl:3-22) + the dot pack of the trial kernel (same terms, same order)
@@ -137,16 +167,17 @@ struct Problem {
                 acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].x * u[j].x;     acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].y * u[j].y;
             }
         }
-        cta_allreduce<9>(acc, scratch, phase);
+        allreduce<9>(acc);
 #pragma unroll
         for (int k = 0; k < 9; ++k) P.v[k] = acc[k];
         evals++;
     }
 };
 
+// ---------------------------------------------------------------- StrongWolfeBisection
 // zoom! (nocedal.jl:162-209)
-template <int NPT>
-__device__ int zoom(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c, double a_lb, double a_ub,
+template <class PB>
+__device__ int zoom(PB &S, Pack9 &P, const cgo_batched_config &c, double a_lb, double a_ub,
                     double phi_lb, double phi0, double dphi0, int64_t evals, double &phi_out, double &a_out,
                     int64_t &evals_out) {
     double a = 0.0, phi_a = 0.0, dphi_a = 0.0;
@@ -172,9 +203,9 @@ __device__ int zoom(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c, doub
 }
 
 // linesearch! (nocedal.jl:33-158); dphi0 = dot(df_x, u) was reduced by update_dir
-template <int NPT>
-__device__ int linesearch(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0,
-                          double a_initial, double &phi_out, double &a_out, int64_t &evals_out) {
+template <class PB>
+__device__ int ls_strong_wolfe(PB &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0,
+                               double a_initial, double &phi_out, double &a_out, int64_t &evals_out) {
     if (!(0.0 < a_initial && isfinite(a_initial))) a_initial = 1.0;        // :49-52
     const double phi0 = f_x;
     if (dphi0 > 0.0) {                                                      // :57-63
@@ -212,6 +243,147 @@ __device__ int linesearch(Problem<NPT> &S, Pack9 &P, const cgo_batched_config &c
     return CGO_ST_LS_MAX_ITERS;                                             // :157
 }
 
+// ---------------------------------------------------------------- WolfeBisection
+// findfeasiblestepsize! (wolfe.jl:171-207): 0 feasible, 1 infeasible, 2 lower bound above the step
+template <class PB>
+__device__ int find_feasible(PB &S, Pack9 &P, int64_t &evals, double &a, double reduction, double lb,
+                             int64_t max_iters, double &phi_a, double &dphi_a) {
+    if (lb > a) { phi_a = 0.0; dphi_a = 0.0; return 2; }                    // :186-188
+    S.eval_trial(a, P);                                                     // :191
+    phi_a = P.v[CGO_P_PHI]; dphi_a = P.v[CGO_P_DPHI];
+    evals += 1;
+    int64_t iter = 1;
+    while (a > lb && iter < max_iters) {                                    // :195
+        if (isfinite(phi_a) && isfinite(dphi_a)) return 0;
+        a = a * reduction;                                                  // :200
+        S.eval_trial(a, P);
+        phi_a = P.v[CGO_P_PHI]; dphi_a = P.v[CGO_P_DPHI];
+        evals += 1;
+        iter += 1;
+    }
+    return 1;                                                               // :206
+}
+// evalwolfeconditions (wolfe.jl:219-251 YuanWeiLuWolfe, :264-294 Wolfe); uu = dot(u, u) (:240)
+__device__ __forceinline__ void eval_wolfe(const cgo_batched_config &c, double phi_a, double dphi_a, double a,
+                                           double uu, double phi0, double dphi0, bool &valid_large, bool &valid_small) {
+    if (c.linesearch == 2) {
+        const double t1 = -c.delta1 * dphi0, t2 = c.c1 * a * uu / 2;
+        const double rhs1 = phi0 + c.c1 * a * dphi0 + a * jl_min(t1, t2);   // :243
+        valid_large = phi_a <= rhs1;
+        const double t3 = c.c1 * a * uu;
+        const double rhs2 = c.c2 * dphi0 + jl_min(t1, t3);                  // :247
+        valid_small = dphi_a >= rhs2;
+    } else {
+        valid_large = phi_a <= phi0 + c.c1 * a * dphi0;                     // :285-286
+        valid_small = dphi_a >= c.c2 * dphi0;                               // :289-290
+    }
+}
+// linesearch! (wolfe.jl:13-165), quirks included: the reset u ← −df_x at :123-129 keeps the old
+// dϕ_0, and the tuple built at :131 is not returned
+template <class PB>
+__device__ int ls_wolfe_bisection(PB &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0, double uu,
+                                  double a_initial, double &phi_out, double &a_out, int64_t &evals_out) {
+    const double reduction = 0.5, growth = 2.0;                             // :23-24
+    const double max_step = c.max_step_size;
+    if (!(max_step > a_initial && a_initial > 0.0)) a_initial = fmin(1.0, max_step / 2);   // :30-32
+    const double phi0 = f_x;
+    phi_out = phi0; a_out = 0.0; evals_out = 0;
+    if (!isfinite(phi0)) return CGO_ST_ACCEPTED_NON_FINITE;                 // :36-38
+    if (dphi0 > 0.0) return CGO_ST_NON_DESCENT;                             // :40-47
+    double a = a_initial;
+    int64_t evals = 0;
+    double lb = 0.0, ub = INFINITY;
+    double phi_a, dphi_a;
+    int st = find_feasible(S, P, evals, a, reduction, 0.0, c.feas_max_iters, phi_a, dphi_a);   // :51-62
+    if (st != 0) return CGO_ST_NO_INITIAL_FEASIBLE;
+    for (int64_t it = 0; it < c.ls_max_iters; ++it) {                       // :67
+        bool vl, vs;
+        eval_wolfe(c, phi_a, dphi_a, a, uu, phi0, dphi0, vl, vs);           // :70-78
+        if (!vl || !vs) {
+            if (!vl) {
+                ub = a;                                                     // :86
+                a = (lb + ub) / 2;                                          // :95
+            } else {
+                lb = a;                                                     // :98
+                if (!isfinite(ub)) {
+                    a = growth * a;                                         // :102
+                    if (a > max_step) return CGO_ST_MAX_STEP_LENGTH;        // :104-112
+                } else {
+                    a = (lb + ub) / 2;                                      // :114
+                }
+            }
+            if (!(lb < a && a < ub)) {                                      // :122
+                const double nrm = sqrt(S.norm_sq_u_plus_g());              // :123
+                if (!(nrm == 0.0)) {
+                    lb = 0.0; ub = INFINITY;
+                    a = a_initial;
+                    double gu_unused;
+                    S.update_dir(0.0, true, gu_unused, uu);                 // :129  u[:] = −df_x (dϕ_0 kept)
+                }
+            }
+            st = find_feasible(S, P, evals, a, reduction, lb, c.feas_max_iters, phi_a, dphi_a);   // :141-152
+            if (st != 0) return CGO_ST_NO_FEASIBLE_STEP;                    // :157
+        } else {
+            phi_out = phi_a; a_out = a; evals_out = evals;                  // :160
+            return CGO_ST_SUCCESS;
+        }
+    }
+    phi_out = phi_a; a_out = a; evals_out = evals;
+    return CGO_ST_LS_MAX_ITERS;                                             // :164
+}
+
+// ---------------------------------------------------------------- Backtracking (Armijo)
+__device__ __forceinline__ bool eval_armijo(double c1, double phi_a, double a, double phi0, double dphi0) {
+    if (!isfinite(phi0) || !isfinite(phi_a) || !isfinite(a)) return false;  // geometric.jl:177-179
+    return (phi0 - phi_a) >= -c1 * a * dphi0;                               // :182-183
+}
+// linesearch! + geometricsearch! (geometric.jl:22-152), bug-for-bug: :success returns the PREVIOUS
+// (ϕ, a) while xp / g⁺ hold the rejected trial, which the engine then adopts (optim.jl:136-139)
+template <class PB>
+__device__ int ls_backtracking(PB &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0, double uu,
+                               double a_initial, double &phi_out, double &a_out, int64_t &evals_out) {
+    const double phi0 = f_x;
+    phi_out = phi0; a_out = 0.0; evals_out = 0;
+    if (!isfinite(phi0)) return CGO_ST_ACCEPTED_NON_FINITE;                 // :39-41
+    if (dphi0 > 0.0) return CGO_ST_NON_DESCENT;                             // :43-48
+    int64_t evals = 0;
+    double a = a_initial;
+    if (!isfinite(a)) a = fabs(phi0) / uu;                                  // :50-53
+    if (!isfinite(a)) a = 1.0;                                              // :54-57
+    double phi_a, dphi_a;
+    int st = find_feasible(S, P, evals, a, 0.5, 0.0, c.feas_max_iters, phi_a, dphi_a);   // :60-71
+    if (st != 0) return CGO_ST_NO_INITIAL_FEASIBLE;                         // :74
+    S.eval_trial(a, P);                                                     // :78 (redundant re-evaluation)
+    phi_a = P.v[CGO_P_PHI];
+    evals += 1;
+    const bool divide = eval_armijo(c.c1, phi_a, a, phi0, dphi0);           // :81-97
+    double a_prev = a, phi_prev = phi_a;
+    for (int64_t it = 0; it < c.ls_max_iters; ++it) {                       // geometricsearch! :102-152
+        a = divide ? a / c.discount : a * c.discount;                       // :127
+        if (!isfinite(a)) { phi_out = phi_prev; a_out = a_prev; evals_out = evals; return CGO_ST_NON_FINITE_STEP; }
+        if (a == a_prev) { phi_out = phi_prev; a_out = a_prev; evals_out = evals; return CGO_ST_SAME_STEP; }
+        S.eval_trial(a, P);                                                 // :137
+        phi_a = P.v[CGO_P_PHI];
+        evals += 1;
+        if (!eval_armijo(c.c1, phi_a, a, phi0, dphi0)) {                    // :140-144
+            phi_out = phi_prev; a_out = a_prev; evals_out = evals;
+            return CGO_ST_SUCCESS;
+        }
+        a_prev = a; phi_prev = phi_a;
+    }
+    phi_out = phi_a; a_out = a; evals_out = evals;
+    return CGO_ST_LS_MAX_ITERS;                                             // :151
+}
+
+template <class PB>
+__device__ __forceinline__ int linesearch(PB &S, Pack9 &P, const cgo_batched_config &c, double f_x, double dphi0,
+                                          double uu, double a_initial, double &phi_out, double &a_out,
+                                          int64_t &evals_out) {
+    if (c.linesearch == 0) return ls_strong_wolfe(S, P, c, f_x, dphi0, a_initial, phi_out, a_out, evals_out);
+    if (c.linesearch == 3) return ls_backtracking(S, P, c, f_x, dphi0, uu, a_initial, phi_out, a_out, evals_out);
+    return ls_wolfe_bisection(S, P, c, f_x, dphi0, uu, a_initial, phi_out, a_out, evals_out);
+}
+
 // getβ from the dot pack (the single-pass forms of conjugategradientoptim.jl_b200/cg_flavours.py)
 __device__ __forceinline__ double get_beta(const cgo_batched_config &c, const Pack9 &P) {
     const double *v = P.v;
@@ -247,12 +419,17 @@ struct BatchedOut {
     int32_t *status;
 };
 
-template <int NPT>
-__global__ void __launch_bounds__(BT, NPT == 1 ? 3 : (NPT == 2 ? 2 : 1))
+constexpr int batched_occ(int npt, int nwarp) {       // CTAs per SM the register budget allows
+    return nwarp == 1 ? (npt <= 2 ? 16 : 8) : (nwarp == 2 ? 4 : (nwarp == 4 ? 2 : 1));
+}
+
+template <int NPT, int NWARP>
+__global__ void __launch_bounds__(32 * NWARP, batched_occ(NPT, NWARP))
 k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_batched_config c, BatchedOut out) {
-    __shared__ double scratch[9 * NW + 2 * 9];
+    constexpr int BT = 32 * NWARP;
+    __shared__ double scratch[NWARP > 1 ? 9 * NWARP + 2 * 9 : 1];
     for (int64_t prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
-        Problem<NPT> S;
+        Problem<NPT, NWARP> S;
         S.n = n; S.scratch = scratch; S.phase = 0; S.evals = 0;
         const double2 *xin = reinterpret_cast<const double2 *>(x0 + prob * (int64_t)n);
 #pragma unroll
@@ -263,7 +440,8 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
         S.eval_initial(f_x, gg);                                            // :25
         double norm_g = sqrt(gg);                                           // :26
         const double f_x0 = f_x;                                            // :31
-        double dphi0 = S.update_dir(0.0, true);                             // :46  u = −g
+        double dphi0, uu;
+        S.update_dir(0.0, true, dphi0, uu);                                 // :46  u = −g
         double a_initial = nan("");                                         // :47
         int status = CGO_ST_MAX_ITERS_REACHED;
         int64_t iters_ran = c.max_iters;
@@ -276,7 +454,7 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
             }
             double f_xp, a_star;
             int64_t evals;
-            const int st = linesearch(S, P, c, f_x, dphi0, a_initial, f_xp, a_star, evals);   // :83
+            const int st = linesearch(S, P, c, f_x, dphi0, uu, a_initial, f_xp, a_star, evals);   // :83
             a_initial = a_star;                                             // :92
             if (st != CGO_ST_SUCCESS) { status = st; iters_ran = it - 1; break; }            // :93-104
             const double norm_gp = sqrt(P.v[CGO_P_GPGP]);                   // :107
@@ -287,7 +465,7 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
 #pragma unroll
             for (int j = 0; j < NPT; ++j) { S.x[j] = S.xp[j]; S.g[j] = S.gp[j]; }             // :136-140
             f_x = f_xp; norm_g = norm_gp;                                   // :138, :141
-            dphi0 = S.update_dir(beta, false);                              // :145
+            S.update_dir(beta, false, dphi0, uu);                           // :145
         }
         // Results (types.jl:107-151)
         double2 *xout = out.minimizer ? reinterpret_cast<double2 *>(out.minimizer + prob * (int64_t)n) : nullptr;
@@ -304,8 +482,17 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
             if (out.status) out.status[prob] = status;
             if (out.fdf_evals) out.fdf_evals[prob] = S.evals;
         }
-        __syncthreads();
+        if (NWARP > 1) __syncthreads();
     }
+}
+
+template <int NPT, int NWARP>
+static void launch_batched(cgo_ctx *ctx, int64_t nprob, int n, const double *d_x0, const cgo_batched_config &cfg,
+                           const BatchedOut &o) {
+    // dynamic distribution is not worth an atomic per problem: a few waves of persistent CTAs
+    const int64_t cap = (int64_t)ctx->sms * batched_occ(NPT, NWARP) * 4;
+    const int grid = (int)(nprob < cap ? nprob : cap);
+    k_batched_rosenbrock<NPT, NWARP><<<grid, 32 * NWARP, 0, ctx->stream>>>(nprob, n, d_x0, cfg, o);
 }
 
 template <class T>
@@ -316,16 +503,37 @@ int dev_alloc(T **p, size_t count) {
 
 }  // namespace
 
+// lanes per problem: the fewest warps (1, 2, 4, 8) that keep at most 8 element pairs per lane
+extern "C" int cgo_batched_layout(int32_t n, int32_t *nwarp, int32_t *pairs_per_lane) {
+    CGO_CHECK(nwarp && pairs_per_lane && n >= 2, "bad arguments");
+    const int pairs = (n + 1) / 2;
+    int w = 1;
+    while (w < 8 && pairs > 32 * w * 8) w *= 2;
+    *nwarp = w;
+    *pairs_per_lane = (pairs + 32 * w - 1) / (32 * w);
+    return 0;
+}
+
 extern "C" int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int32_t n, const double *x0,
                                                const cgo_batched_config *cfg, double *objective,
                                                int64_t *iters_ran, int32_t *status, int64_t *fdf_evals,
                                                double *minimizer, double *grad_norm) {
     CGO_CHECK(ctx && x0 && cfg, "NULL argument");
     CGO_CHECK(nprob >= 0, "nprob < 0");
-    CGO_CHECK(n >= 2 && n % 2 == 0 && n <= 2 * BT * CGO_U_VEC, "n must be even and in [2, %d]", 2 * BT * CGO_U_VEC);
+    CGO_CHECK(n >= 2 && n % 2 == 0 && n <= 4096, "n must be even and in [2, 4096]");
     CGO_CHECK(0.0 < cfg->eps && cfg->eps < 1.0, "need 0 < eps < 1 (types.jl:187)");
-    CGO_CHECK(0.0 < cfg->c1 && cfg->c1 < cfg->c2 && cfg->c2 < 1.0 && cfg->growth > 1.0 && cfg->ls_max_iters >= 0 &&
-                  cfg->zoom_max_iters >= 0, "StrongWolfeBisection config asserts failed (nocedal.jl:22-26)");
+    CGO_CHECK(cfg->linesearch >= 0 && cfg->linesearch <= 3, "linesearch %d out of [0,3]", cfg->linesearch);
+    if (cfg->linesearch == 0)
+        CGO_CHECK(0.0 < cfg->c1 && cfg->c1 < cfg->c2 && cfg->c2 < 1.0 && cfg->growth > 1.0 && cfg->ls_max_iters >= 0 &&
+                      cfg->zoom_max_iters >= 0, "StrongWolfeBisection config asserts failed (nocedal.jl:22-26)");
+    else if (cfg->linesearch == 1)
+        CGO_CHECK(0.0 < cfg->c1 && cfg->c1 < cfg->c2 && cfg->c2 < 1.0, "Wolfe needs 0 < c1 < c2 < 1 (wolfe.jl:278)");
+    else if (cfg->linesearch == 2)
+        CGO_CHECK(0.0 < cfg->delta1 && cfg->delta1 < cfg->c1 && cfg->c1 < cfg->c2 && cfg->c2 < 1.0,
+                  "YuanWeiLuWolfe needs 0 < delta1 < c1 < c2 < 1 (wolfe.jl:233)");
+    else
+        CGO_CHECK(0.0 < cfg->c1 && cfg->c1 < 1.0 && 0.0 < cfg->discount && cfg->discount < 1.0,
+                  "Armijo needs 0 < c1 < 1 (geometric.jl:174) and a discount factor in (0,1)");
     CGO_CHECK(cfg->flavour >= 0 && cfg->flavour <= 3, "flavour %d out of [0,3]", cfg->flavour);
     if (nprob == 0) return 0;
     CGO_CUDA(cudaSetDevice(ctx->device));
@@ -343,14 +551,16 @@ extern "C" int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int3
         if (fdf_evals) CGO_TRY(dev_alloc(&o.fdf_evals, (size_t)nprob));
         if (status) CGO_TRY(dev_alloc(&o.status, (size_t)nprob));
         if (minimizer) CGO_TRY(dev_alloc(&o.minimizer, nx));
-        const int npt = (n + 2 * BT - 1) / (2 * BT);                        // double2 items per lane
-        const int occ = npt <= 1 ? 3 : (npt <= 2 ? 2 : 1);
-        int64_t cap = (int64_t)ctx->sms * occ * 4;                          // a few waves of persistent CTAs
-        const int grid = (int)(nprob < cap ? nprob : cap);
+        int nwarp, npt;
+        cgo_batched_layout(n, &nwarp, &npt);
         cgo_timer_begin(ctx, CGO_T_BATCHED);
-        if (npt <= 1) k_batched_rosenbrock<1><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
-        else if (npt <= 2) k_batched_rosenbrock<2><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
-        else k_batched_rosenbrock<4><<<grid, BT, 0, s>>>(nprob, n, d_x0, *cfg, o);
+        if (nwarp == 1 && npt <= 1) launch_batched<1, 1>(ctx, nprob, n, d_x0, *cfg, o);
+        else if (nwarp == 1 && npt <= 2) launch_batched<2, 1>(ctx, nprob, n, d_x0, *cfg, o);
+        else if (nwarp == 1 && npt <= 4) launch_batched<4, 1>(ctx, nprob, n, d_x0, *cfg, o);
+        else if (nwarp == 1) launch_batched<8, 1>(ctx, nprob, n, d_x0, *cfg, o);
+        else if (nwarp == 2) launch_batched<8, 2>(ctx, nprob, n, d_x0, *cfg, o);
+        else if (nwarp == 4) launch_batched<8, 4>(ctx, nprob, n, d_x0, *cfg, o);
+        else launch_batched<8, 8>(ctx, nprob, n, d_x0, *cfg, o);
         cgo_timer_end(ctx);
         ctx->launches++;
         CGO_CUDA(cudaGetLastError());

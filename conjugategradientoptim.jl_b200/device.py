@@ -433,30 +433,50 @@ class BatchedResults:
         return [STATUS_SYMBOLS[c] for c in self.status_code]
 
 
+def batched_lanes(n: int) -> int:
+    """Lanes (CTA size) the batched kernel gives a problem of dimension n: its reductions follow the
+    canonical order with this many lanes and one tile (include/cgoptim.h)."""
+    nw, npt = C.c_int32(), C.c_int32()
+    check(lib().cgo_batched_layout(int(n), C.byref(nw), C.byref(npt)))
+    return 32 * nw.value
+
+
 def minimizeobjective_batched(x_initial, config, linesearch_config, ctx: Optional[Context] = None,
                               want_minimizer: bool = True) -> BatchedResults:
     """`minimizeobjective` (src/engine/optim.jl:6-171) for MANY independent extended-Rosenbrock
     problems at once (BASELINE.json configs[4]): `x_initial` is (nprob, n), one CTA solves one
-    problem entirely on the device (StrongWolfeBisection line search, any of the four CG
-    flavours), no communication between problems."""
+    problem entirely on the device — any of the four CG flavours (cg_flavours.jl) with any of the
+    line searches (StrongWolfeBisection, WolfeBisection{Wolfe | YuanWeiLuWolfe},
+    Backtracking{Armijo}) — no communication between problems."""
     from .cg_flavours import HagerZhang, LiuStorrey, SallehAlhawarat, YuanWangSheng
+    from .linesearch.geometric import Armijo, Backtracking
     from .linesearch.nocedal import StrongWolfeBisection
+    from .linesearch.wolfe import Wolfe, WolfeBisection, YuanWeiLuWolfe
     ctx = ctx or default_context()
     X0 = np.ascontiguousarray(x_initial, dtype=np.float64)
     if X0.ndim != 2:
         raise ValueError("x_initial must be (nprob, n)")
     nprob, n = X0.shape
-    if not isinstance(linesearch_config, StrongWolfeBisection):
-        raise TypeError("the batched solver implements StrongWolfeBisection (SURVEY.md §8f N2 lists the others as next)")
     β = config.β_config
     flav = {HagerZhang: 0, YuanWangSheng: 1, SallehAlhawarat: 2, LiuStorrey: 3}.get(type(β))
     if flav is None:
         raise TypeError(f"the batched solver has no {type(β).__name__} flavour")
-    bc = capi.BatchedConfig(eps=config.ϵ, max_iters=config.max_iters, flavour=flav, _pad=0,
-                            mu=getattr(β, "μ", 0.0), c1=linesearch_config.c1, c2=linesearch_config.c2,
-                            growth=linesearch_config.a_max_growth_factor,
-                            ls_max_iters=linesearch_config.max_iters,
-                            zoom_max_iters=linesearch_config.zoom_max_iters)
+    ls = linesearch_config
+    bc = capi.BatchedConfig(eps=config.ϵ, max_iters=config.max_iters, flavour=flav, mu=getattr(β, "μ", 0.0),
+                            c1=0.0, c2=0.0, growth=2.0, ls_max_iters=getattr(ls, "max_iters", 0), zoom_max_iters=0,
+                            delta1=0.0, max_step_size=0.0, discount=0.5, feas_max_iters=0)
+    if isinstance(ls, StrongWolfeBisection):
+        bc.linesearch, bc.c1, bc.c2, bc.growth = 0, ls.c1, ls.c2, ls.a_max_growth_factor
+        bc.zoom_max_iters = ls.zoom_max_iters
+    elif isinstance(ls, WolfeBisection) and isinstance(ls.condition, (Wolfe, YuanWeiLuWolfe)):
+        bc.linesearch = 2 if isinstance(ls.condition, YuanWeiLuWolfe) else 1
+        bc.c1, bc.c2, bc.delta1 = ls.condition.c1, ls.condition.c2, getattr(ls.condition, "δ1", 0.0)
+        bc.max_step_size, bc.feas_max_iters = ls.max_step_size, ls.feasibility_max_iters
+    elif isinstance(ls, Backtracking) and isinstance(ls.condition, Armijo):
+        bc.linesearch, bc.c1, bc.discount = 3, ls.condition.c1, ls.discount_factor
+        bc.feas_max_iters = ls.feasibility_max_iters
+    else:
+        raise TypeError(f"no batched linesearch! method for {type(ls).__name__}")
     obj, gn = np.empty(nprob), np.empty(nprob)
     it, ev = np.empty(nprob, dtype=np.int64), np.empty(nprob, dtype=np.int64)
     st = np.empty(nprob, dtype=np.int32)

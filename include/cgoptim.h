@@ -179,18 +179,26 @@ int cgo_download_vector(cgo_state *st, int32_t which, double *host);
 
 /* ---------------------------------------------------------------- batched solver ----------
  * SURVEY.md §8 cfg 5: many independent small problems, the whole of minimizeobjective
- * (optim.jl:6-171) + StrongWolfeBisection (nocedal.jl:33-209) + getβ (cg_flavours.jl) on the
- * device, one CTA per problem, all five n-vectors in shared memory.                        */
+ * (optim.jl:6-171) + any of the three line searches (nocedal.jl, wolfe.jl, geometric.jl) + getβ
+ * (cg_flavours.jl) on the device, one CTA per problem, all five n-vectors in registers.     */
 typedef struct {
     double eps;             /* CGConfig.ϵ            types.jl:161 */
     int64_t max_iters;      /* CGConfig.max_iters    types.jl:164 */
     int32_t flavour;        /* 0 HagerZhang, 1 YuanWangSheng, 2 SallehAlhawarat, 3 LiuStorrey */
-    int32_t _pad;
+    int32_t linesearch;     /* 0 StrongWolfeBisection (nocedal.jl), 1 WolfeBisection{Wolfe}, 2 WolfeBisection{YuanWeiLuWolfe}
+                               (wolfe.jl), 3 Backtracking{Armijo} (geometric.jl) */
     double mu;              /* YuanWangSheng.μ */
-    double c1, c2, growth;  /* StrongWolfeBisection   nocedal.jl:3-11 */
+    double c1, c2, growth;  /* c1 (all), c2 (0-2), a_max_growth_factor (0)   nocedal.jl:3-11, wolfe.jl:213-262, geometric.jl:159 */
     int64_t ls_max_iters, zoom_max_iters;
+    double delta1;          /* YuanWeiLuWolfe.δ1                 wolfe.jl:216 */
+    double max_step_size;   /* WolfeBisection.max_step_size      wolfe.jl:9   */
+    double discount;        /* Backtracking.discount_factor      geometric.jl:17 */
+    int64_t feas_max_iters; /* feasibility_max_iters             wolfe.jl:10, geometric.jl:19 */
 } cgo_batched_config;
-/* extended Rosenbrock problems of dimension n (even, <= 1024); x0 is nprob×n row-major on the
+/* lanes per problem of the batched kernel: the fewest warps (1, 2, 4, 8) that keep at most eight
+ * element pairs per lane; its reductions follow the canonical order with B = 32·nwarp lanes, one tile */
+int cgo_batched_layout(int32_t n, int32_t *nwarp, int32_t *pairs_per_lane);
+/* extended Rosenbrock problems of dimension n (even, <= 4096); x0 is nprob×n row-major on the
  * host.  Outputs (host, any may be NULL): objective[nprob], iters_ran[nprob], status[nprob],
  * fdf_evals[nprob], minimizer[nprob×n], grad_norm[nprob]. */
 int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int32_t n, const double *x0,

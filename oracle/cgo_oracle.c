@@ -77,11 +77,25 @@ static double dot_comp(const double *a, const double *b, int64_t n) { /* Neumaie
  * warp and then sequentially over warps; the grid combines the min(G, ntiles) CTA partials the
  * same way (lane t takes partials t, t+B, ...).  Shards (ranks) each reduce their contiguous
  * slice this way and the shard results are added in rank order.                            */
-enum { CGO_B = 256 };
+enum { CGO_BMAX = 256 };
 static int g_cgo_G = 296, g_cgo_shards = 1;
+/* lanes per virtual CTA: 256 everywhere except the batched on-device solver, whose CTA is as small
+ * as eight element pairs per lane allow (32, 64, 128 or 256 lanes; include/cgoptim.h) */
+static int CGO_B = 256;
 void orc_set_cgo_order(int G, int shards) { g_cgo_G = G > 0 ? G : 296; g_cgo_shards = shards > 0 ? shards : 1; }
+/* items per lane and tile of the BLAS-1 mapping: 4 double2 loads (k_blas1), 8 in the batched solver */
+static int g_blas1_U = 4;
+static int g_site_V = 2, g_site_U = 4;
+void orc_set_cgo_lanes(int B) {
+    CGO_B = (B == 32 || B == 64 || B == 128) ? B : 256;
+    g_blas1_U = 4; g_site_V = 2; g_site_U = 4;
+}
+void orc_set_cgo_batched(int B) {       /* the batched solver's order: B lanes, every item in ONE tile */
+    CGO_B = (B == 32 || B == 64 || B == 128) ? B : 256;
+    g_blas1_U = 8; g_site_V = 2; g_site_U = 8;
+}
 static double cgo_cta_combine(double *lane /* CGO_B, clobbered */) {
-    double wsum[CGO_B / 32];
+    double wsum[CGO_BMAX / 32];
     for (int w = 0; w < CGO_B / 32; ++w) {
         double *v = lane + 32 * w, t[32];
         for (int off = 16; off >= 1; off >>= 1) {
@@ -110,7 +124,7 @@ static double cgo_reduce_slice(term_fn f, const void *ctx, int64_t lo, int64_t c
     }
     double *P = (double *)calloc((size_t)nact, sizeof(double));
     for (int c = 0; c < nact; ++c) P[c] = cgo_cta_combine(acc + (size_t)c * CGO_B);
-    double lane[CGO_B];
+    double lane[CGO_BMAX];
     for (int t = 0; t < CGO_B; ++t) {
         double s2 = 0.0;
         for (int k = t; k < nact; k += CGO_B) s2 = s2 + P[k];
@@ -144,7 +158,6 @@ static double sum_term(const void *c, int64_t i) { return ((const double *)c)[i]
 /* BLAS-1 kernels read vectors as 128-bit double2 (V=2) with U=4 loads per lane per tile;
  * row-per-lane (CSR) kernels use V=1, U=1.  g_site_V/U select the mapping of the kernel that
  * computes the reduction at the current call site (see DESIGN.md "reduction sites"). */
-static int g_site_V = 2, g_site_U = 4;
 void orc_set_site(int V, int U) { g_site_V = V; g_site_U = U; }
 static double dot_cgo(const double *a, const double *b, int64_t n) {
     dot_ctx d = {a, b};
@@ -196,7 +209,7 @@ double orc_sum_cgo(const double *a, int64_t n, int U, int64_t align) {
     return cgo_reduce(sum_term, a, n, 1, U, align);
 }
 double orc_sum(const double *a, int64_t n, int mode, int threads) {
-    if (mode == ORC_SUM_CGO) return orc_sum_cgo(a, n, 4, 1);
+    if (mode == ORC_SUM_CGO) return orc_sum_cgo(a, n, g_blas1_U, 1);
     if (threads <= 1 || n < 4096) return sum_mode_(a, n, mode);
     double *part = (double *)calloc((size_t)threads, sizeof(double));
 #pragma omp parallel for num_threads(threads) schedule(static, 1)
@@ -345,7 +358,7 @@ static double logreg_fdf(orc_objective *o, double *g, const double *w) {
     free(lp);
     csr_mv(o->n, o->rowptrT, o->colT, o->valT, c, g, o->threads);
     int sv = g_site_V, su = g_site_U;
-    g_site_V = 2; g_site_U = 4;                 /* w·w is reduced by the BLAS-1 kernel K_a */
+    g_site_V = 2; g_site_U = g_blas1_U;         /* w·w is reduced by the BLAS-1 kernel K_a */
     double ww = orc_dot(w, w, o->n, o->sum_mode, o->threads);
     g_site_V = sv; g_site_U = su;
     double invN = 1.0 / (double)N;
@@ -559,10 +572,10 @@ typedef struct {
  * BLAS-1 kernel (V=2,U=4); SITE_TRIAL = reduced inside the objective's trial kernels */
 enum { SITE_BLAS1 = 0, SITE_TRIAL = 1 };
 static inline double vdot_site(const solver *s, const double *a, const double *b, int site) {
-    if (site == SITE_TRIAL) { g_site_V = s->obj->trial_V; g_site_U = s->obj->trial_U; }
-    else { g_site_V = 2; g_site_U = 4; }
+    if (site == SITE_TRIAL) { g_site_V = s->obj->trial_V; g_site_U = s->obj->trial_V == 2 ? g_blas1_U : s->obj->trial_U; }
+    else { g_site_V = 2; g_site_U = g_blas1_U; }
     double r = orc_dot(a, b, s->info.n, s->cfg->sum_mode, s->cfg->threads);
-    g_site_V = 2; g_site_U = 4;
+    g_site_V = 2; g_site_U = g_blas1_U;
     return r;
 }
 static inline double vdot(const solver *s, const double *a, const double *b) {

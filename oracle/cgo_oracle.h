@@ -120,6 +120,8 @@ double orc_dot(const double *a, const double *b, int64_t n, int sum_mode, int th
 double orc_sum(const double *a, int64_t n, int sum_mode, int threads);
 double orc_sum_cgo(const double *a, int64_t n, int U, int64_t align);
 void orc_set_cgo_order(int G, int shards);   /* canonical-order parameters (global) */
+void orc_set_cgo_lanes(int B);               /* lanes per virtual CTA (default 256), BLAS-1 tiles of 4 double2 per lane */
+void orc_set_cgo_batched(int B);             /* order of the batched solver: B = 32..256 lanes, all items in one tile */
 void orc_spmv(const orc_objective *, int transposed, const double *x, double *y);
 double orc_hash_u01(uint64_t seed, uint64_t i, uint64_t k);
 void orc_rosenbrock_x0(int64_t n, uint64_t seed, double perturb, double *x0);

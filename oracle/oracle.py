@@ -97,6 +97,10 @@ def lib():
     L.orc_obj_set_sum_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_obj_trial_site.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_set_site.argtypes = [C.c_int, C.c_int]
+    L.orc_set_cgo_lanes.argtypes = [C.c_int]
+    L.orc_set_cgo_lanes.restype = None
+    L.orc_set_cgo_batched.argtypes = [C.c_int]
+    L.orc_set_cgo_batched.restype = None
     L.orc_spmv.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.orc_hash_u01.restype = C.c_double
     L.orc_hash_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
@@ -241,6 +245,16 @@ def dot(a, b, sum_mode="seq", threads=1):
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     return lib().orc_dot(_dp(a), _dp(b), a.size, SUM_MODES[sum_mode], threads)
+
+
+def set_cgo_lanes(B=256):
+    """lanes per virtual CTA of the canonical order (default; also undoes set_cgo_batched)"""
+    lib().orc_set_cgo_lanes(int(B))
+
+
+def set_cgo_batched(B):
+    """reduction order of the batched on-device solver: B lanes, every item in one tile"""
+    lib().orc_set_cgo_batched(int(B))
 
 
 def set_cgo_order(G=296, shards=1):
