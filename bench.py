@@ -503,13 +503,21 @@ def run_batched(args):
                            "problems_per_s": round(nprob * world * K / (kms * 1e-3), 1),
                            "iterations_total": tot_it, "fdf_evals_total": tot_ev, "converged": tot_ok,
                            "l2_policy": "on-chip workload: x0 read once, result written once (HBM roofline not applicable)"},
-                "roofline": {"bound": "on-chip latency (registers + shuffles); HBM roofline not applicable", "achieved": None,
-                             "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                             "fp64_gflops_estimate": round(tot_ev * K * (n / 2) * 49 / (kms * 1e-3) / 1e9, 1)},
+                # FP64 instructions the kernel issues per element pair and trial (Hager-Zhang: x + a u 4, objective and
+                # gradient 12, y 2, six dots 25); no FMA anywhere (the reference's arithmetic is unfused), so the
+                # pipe's ceiling is one DADD/DMUL per FP64 lane and clock: 64 lanes x SMs x max SM clock
+                "roofline": {"bound": "fp64 pipe (on-chip: registers + shuffles; HBM roofline not applicable)",
+                             "achieved": round(tot_ev * K * (n / 2) * 43 / (kms * 1e-3) / 1e12, 3),
+                             "peak": round(64 * ctx.sm_count * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12, 3)
+                             if clocks and clocks.get("sm_max_mhz") else round(64 * ctx.sm_count * 1965e6 / 1e12, 3),
+                             "unit": "TFLOP/s (unfused FP64 instructions)", "frac": None, "traffic": None,
+                             "peak_source": "nominal: 64 FP64 lanes/SM/clk x SM count x max SM clock, FMA not usable"},
                 "e2e": {"value": round(tot_it * K / wall, 1), "unit": "iterations/s",
                         "h2d_bytes_per_step": 8.0 * nprob * n, "d2h_bytes_per_step": 8.0 * nprob * n + 36.0 * nprob,
                         "includes": "x0 H2D from pinned memory, solve, minimizers + per-problem results D2H"},
                 "gpu_launches": int(ctx.kernel_launches - l0), "clocks": clocks, "cpu_baseline": None}
+    if line is not None and line["roofline"]["peak"]:
+        line["roofline"]["frac"] = round(line["roofline"]["achieved"] / line["roofline"]["peak"], 4)
     return line, ctx
 
 

@@ -43,10 +43,20 @@ __device__ __forceinline__ double jl_min(double a, double b) {     // Julia min:
 // order: the canonical order of include/cgoptim.h with B = BT lanes and a single tile.  The
 // launcher picks the fewest warps that keep NPT <= 8, so that n <= 512 (the BASELINE config)
 // runs on ONE warp: every reduction is five shuffles, no shared memory, no barrier.
-template <int NPT, int NWARP>
+// DOTS: bit k set = pack entry k is reduced.  Every flavour needs ϕ, dϕ and ‖g⁺‖²; the other six
+// dots only where its getβ reads them (an entry that is not reduced stays 0 and is never read).
+constexpr int DOTS_ALL = 0x1FF;
+constexpr int dots_of(int flavour) {
+    return flavour == 0 || flavour == 3 ? 0x03F                               // HagerZhang, LiuStorrey: + y·y, u·y, y·g⁺
+         : flavour == 1 ? 0x13F                                               // YuanWangSheng: + u·u
+         : 0x0C7;                                                             // SallehAlhawarat: g⁺·g, u·g
+}
+
+template <int NPT, int NWARP, int DOTS = DOTS_ALL>
 struct Problem {
     static constexpr int BT = 32 * NWARP;
-    double2 x[NPT], g[NPT], u[NPT], xp[NPT], gp[NPT];
+    double2 x[NPT], g[NPT], u[NPT];      // xp and g⁺ are not kept: accept() recomputes them from a_last
+    double a_last;
     int n;                              // problem dimension (even)
     double *scratch;                    // NWARP > 1: 9·NWARP + 2·9 doubles of shared memory
     int phase;
@@ -54,11 +64,12 @@ struct Problem {
 
     __device__ __forceinline__ bool owns(int j) const { return 2 * ((int)threadIdx.x + j * BT) < n; }
 
-    // canonical CTA combine, result in every lane
-    template <int K>
+    // canonical CTA combine of the entries selected by MASK, result in every lane
+    template <int K, int MASK = DOTS_ALL>
     __device__ __forceinline__ void allreduce(double (&acc)[K]) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
+            if (!((MASK >> k) & 1)) continue;
             double v = acc[k];
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
@@ -147,30 +158,47 @@ struct Problem {
                 double2 p;
                 p.x = x[j].x + a * u[j].x;
                 p.y = x[j].y + a * u[j].y;
-                xp[j] = p;
                 const double t = p.y - p.x * p.x;
                 const double om = 1.0 - p.x;
                 const double f = (100.0 * t) * t + om * om;
                 double2 gn;
                 gn.x = (-400.0 * p.x) * t - 2.0 * om;
                 gn.y = 200.0 * t;
-                gp[j] = gn;
                 const double y1 = gn.x - g[j].x, y2 = gn.y - g[j].y;
                 acc[CGO_P_PHI] = acc[CGO_P_PHI] + f;
                 acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.x * u[j].x;   acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn.y * u[j].y;
                 acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.x * gn.x;     acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn.y * gn.y;
-                acc[CGO_P_YY] = acc[CGO_P_YY] + y1 * y1;             acc[CGO_P_YY] = acc[CGO_P_YY] + y2 * y2;
-                acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].x * y1;         acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].y * y2;
-                acc[CGO_P_YGP] = acc[CGO_P_YGP] + y1 * gn.x;         acc[CGO_P_YGP] = acc[CGO_P_YGP] + y2 * gn.y;
-                acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.x * g[j].x;     acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.y * g[j].y;
-                acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].x * g[j].x;     acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].y * g[j].y;
-                acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].x * u[j].x;     acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].y * u[j].y;
+                if (DOTS & (1 << CGO_P_YY)) { acc[CGO_P_YY] = acc[CGO_P_YY] + y1 * y1; acc[CGO_P_YY] = acc[CGO_P_YY] + y2 * y2; }
+                if (DOTS & (1 << CGO_P_UY)) { acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].x * y1; acc[CGO_P_UY] = acc[CGO_P_UY] + u[j].y * y2; }
+                if (DOTS & (1 << CGO_P_YGP)) { acc[CGO_P_YGP] = acc[CGO_P_YGP] + y1 * gn.x; acc[CGO_P_YGP] = acc[CGO_P_YGP] + y2 * gn.y; }
+                if (DOTS & (1 << CGO_P_GPG)) { acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.x * g[j].x; acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn.y * g[j].y; }
+                if (DOTS & (1 << CGO_P_UG)) { acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].x * g[j].x; acc[CGO_P_UG] = acc[CGO_P_UG] + u[j].y * g[j].y; }
+                if (DOTS & (1 << CGO_P_UU)) { acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].x * u[j].x; acc[CGO_P_UU] = acc[CGO_P_UU] + u[j].y * u[j].y; }
             }
         }
-        allreduce<9>(acc);
+        allreduce<9, DOTS>(acc);
 #pragma unroll
         for (int k = 0; k < 9; ++k) P.v[k] = acc[k];
         evals++;
+        a_last = a;
+    }
+    // x[:] = info.xp; df_x[:] = info.df_xp (optim.jl:136-140): info.xp / info.df_xp are those of the
+    // LAST evaluated trial (which Backtracking's :success need not be), re-formed here with the very
+    // expressions eval_trial used — bit-identical, and two n-vectors fewer in registers
+    __device__ __forceinline__ void accept() {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (owns(j)) {
+                double2 p;
+                p.x = x[j].x + a_last * u[j].x;
+                p.y = x[j].y + a_last * u[j].y;
+                const double t = p.y - p.x * p.x;
+                const double om = 1.0 - p.x;
+                x[j] = p;
+                g[j].x = (-400.0 * p.x) * t - 2.0 * om;
+                g[j].y = 200.0 * t;
+            }
+        }
     }
 };
 
@@ -420,16 +448,31 @@ struct BatchedOut {
 };
 
 constexpr int batched_occ(int npt, int nwarp) {       // CTAs per SM the register budget allows
-    return nwarp == 1 ? (npt <= 2 ? 16 : 8) : (nwarp == 2 ? 4 : (nwarp == 4 ? 2 : 1));
+    return nwarp == 1 ? (npt <= 4 ? 16 : 12) : (nwarp == 2 ? 6 : (nwarp == 4 ? 3 : 1));
 }
 
-template <int NPT, int NWARP>
+// Problems are handed out through an atomic counter (their iteration counts differ by two orders
+// of magnitude: a static split leaves most of the grid idle behind the slowest CTAs).
+template <int NPT, int NWARP, int DOTS>
 __global__ void __launch_bounds__(32 * NWARP, batched_occ(NPT, NWARP))
-k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_batched_config c, BatchedOut out) {
+k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_batched_config c, BatchedOut out,
+                     unsigned long long *next_problem) {
     constexpr int BT = 32 * NWARP;
     __shared__ double scratch[NWARP > 1 ? 9 * NWARP + 2 * 9 : 1];
-    for (int64_t prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
-        Problem<NPT, NWARP> S;
+    __shared__ unsigned long long s_prob;
+    for (;;) {
+        unsigned long long pr = 0;
+        if (NWARP == 1) {
+            if (threadIdx.x == 0) pr = atomicAdd(next_problem, 1ULL);
+            pr = __shfl_sync(0xffffffffu, pr, 0);
+        } else {
+            if (threadIdx.x == 0) s_prob = atomicAdd(next_problem, 1ULL);
+            __syncthreads();
+            pr = s_prob;
+        }
+        const int64_t prob = (int64_t)pr;
+        if (prob >= nprob) break;
+        Problem<NPT, NWARP, DOTS> S;
         S.n = n; S.scratch = scratch; S.phase = 0; S.evals = 0;
         const double2 *xin = reinterpret_cast<const double2 *>(x0 + prob * (int64_t)n);
 #pragma unroll
@@ -462,8 +505,7 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
                 status = CGO_ST_NON_FINITE_PROPOSED; iters_ran = it - 1; break;
             }
             const double beta = get_beta(c, P);                             // :130-135
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) { S.x[j] = S.xp[j]; S.g[j] = S.gp[j]; }             // :136-140
+            S.accept();                                                     // :136-140
             f_x = f_xp; norm_g = norm_gp;                                   // :138, :141
             S.update_dir(beta, false, dphi0, uu);                           // :145
         }
@@ -486,13 +528,25 @@ k_batched_rosenbrock(int64_t nprob, int n, const double *__restrict__ x0, cgo_ba
     }
 }
 
+template <int NPT, int NWARP, int DOTS>
+static void launch_batched_dots(cgo_ctx *ctx, int64_t nprob, int n, const double *d_x0, const cgo_batched_config &cfg,
+                                const BatchedOut &o, unsigned long long *counter) {
+    const int64_t cap = (int64_t)ctx->sms * batched_occ(NPT, NWARP);      // every resident slot, once
+    const int grid = (int)(nprob < cap ? nprob : cap);
+    k_batched_rosenbrock<NPT, NWARP, DOTS><<<grid, 32 * NWARP, 0, ctx->stream>>>(nprob, n, d_x0, cfg, o, counter);
+}
 template <int NPT, int NWARP>
 static void launch_batched(cgo_ctx *ctx, int64_t nprob, int n, const double *d_x0, const cgo_batched_config &cfg,
-                           const BatchedOut &o) {
-    // dynamic distribution is not worth an atomic per problem: a few waves of persistent CTAs
-    const int64_t cap = (int64_t)ctx->sms * batched_occ(NPT, NWARP) * 4;
-    const int grid = (int)(nprob < cap ? nprob : cap);
-    k_batched_rosenbrock<NPT, NWARP><<<grid, 32 * NWARP, 0, ctx->stream>>>(nprob, n, d_x0, cfg, o);
+                           const BatchedOut &o, unsigned long long *counter) {
+    if constexpr (NPT == 8 && NWARP == 1) {         // the BASELINE layout (n <= 512): only the dots its flavour reads
+        switch (cfg.flavour) {
+        case 1: return launch_batched_dots<NPT, NWARP, dots_of(1)>(ctx, nprob, n, d_x0, cfg, o, counter);
+        case 2: return launch_batched_dots<NPT, NWARP, dots_of(2)>(ctx, nprob, n, d_x0, cfg, o, counter);
+        default: return launch_batched_dots<NPT, NWARP, dots_of(0)>(ctx, nprob, n, d_x0, cfg, o, counter);
+        }
+    } else {
+        launch_batched_dots<NPT, NWARP, DOTS_ALL>(ctx, nprob, n, d_x0, cfg, o, counter);
+    }
 }
 
 template <class T>
@@ -553,14 +607,16 @@ extern "C" int cgo_batched_minimize_rosenbrock(cgo_ctx *ctx, int64_t nprob, int3
         if (minimizer) CGO_TRY(dev_alloc(&o.minimizer, nx));
         int nwarp, npt;
         cgo_batched_layout(n, &nwarp, &npt);
+        unsigned long long *counter = reinterpret_cast<unsigned long long *>(ctx->d_ticket + 2);
+        CGO_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
         cgo_timer_begin(ctx, CGO_T_BATCHED);
-        if (nwarp == 1 && npt <= 1) launch_batched<1, 1>(ctx, nprob, n, d_x0, *cfg, o);
-        else if (nwarp == 1 && npt <= 2) launch_batched<2, 1>(ctx, nprob, n, d_x0, *cfg, o);
-        else if (nwarp == 1 && npt <= 4) launch_batched<4, 1>(ctx, nprob, n, d_x0, *cfg, o);
-        else if (nwarp == 1) launch_batched<8, 1>(ctx, nprob, n, d_x0, *cfg, o);
-        else if (nwarp == 2) launch_batched<8, 2>(ctx, nprob, n, d_x0, *cfg, o);
-        else if (nwarp == 4) launch_batched<8, 4>(ctx, nprob, n, d_x0, *cfg, o);
-        else launch_batched<8, 8>(ctx, nprob, n, d_x0, *cfg, o);
+        if (nwarp == 1 && npt <= 1) launch_batched<1, 1>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else if (nwarp == 1 && npt <= 2) launch_batched<2, 1>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else if (nwarp == 1 && npt <= 4) launch_batched<4, 1>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else if (nwarp == 1) launch_batched<8, 1>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else if (nwarp == 2) launch_batched<8, 2>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else if (nwarp == 4) launch_batched<8, 4>(ctx, nprob, n, d_x0, *cfg, o, counter);
+        else launch_batched<8, 8>(ctx, nprob, n, d_x0, *cfg, o, counter);
         cgo_timer_end(ctx);
         ctx->launches++;
         CGO_CUDA(cudaGetLastError());
