@@ -15,7 +15,8 @@ from .qn_flavours import LBFGS  # noqa: F401
 from .cg_utils import evalϕdϕ_  # noqa: F401
 from .linesearch import (Armijo, Backtracking, StrongWolfeBisection, Wolfe, WolfeBisection,  # noqa: F401
                          YuanWeiLuWolfe, setupStrongWolfeBisection)
-from .engine import MinimizerRun, minimizeobjective, minimizeobjectivererun  # noqa: F401
+from .engine import (LinesearchSolveSys, MinimizerRun, minimizeobjective, minimizeobjectivererun,  # noqa: F401
+                     setupLinesearchSolveSys, solvesystem)
 from .engine.optim import linesearch_  # noqa: F401
 from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceVector,  # noqa: F401
                      LogRegGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,

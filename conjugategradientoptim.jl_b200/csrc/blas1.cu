@@ -312,6 +312,32 @@ struct GradCombine {
     }
 };
 
+// updateiteratesolvesys! (src/engine/solve_system.jl:237-253): x_next[i] = base[i] + m*df_xp[i]
+// (base = x_next itself as the reference writes it, or x for Alg. 3.1 as published)
+struct SolveSysProject {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 4;
+    struct In { double2 b, g; };
+    const double2 *base, *gp;
+    double2 *xn;
+    double m;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.b = ld2rw(base + q); r.g = cgo_ld2(gp + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 o;
+        o.x = in.b.x + m * in.g.x;
+        o.y = v2 ? in.b.y + m * in.g.y : 0.0;
+        cgo_st2(xn + q, o);
+        acc[0] = acc[0] + o.x * o.x;        // (‖x_next‖², unused: the kernel template reduces K >= 1 sums)
+        if (v2) acc[0] = acc[0] + o.y * o.y;
+    }
+};
+
 // L-BFGS: S = xp − x, Y = g⁺ − g; pack {s·y, y·y}
 struct LbfgsStage {
     static constexpr int TCLASS = CGO_T_LBFGS;
@@ -493,6 +519,7 @@ extern "C" int cgo_state_destroy(cgo_state *st) {
     for (auto p : st->S) cudaFree(p);
     for (auto p : st->Y) cudaFree(p);
     cudaFree(st->q);
+    cudaFree(st->xn);
     delete st;
     return 0;
 }
@@ -645,6 +672,42 @@ int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t s
         red.wait_all = st->ctx->flags_local + CGO_F_GPART; red.wait_val = wait_epoch; red.nranks = st->ctx->nranks;
     }
     return launch_blas1(st->ctx, op, st->n, red);
+}
+
+// ------------------------------------------------------------------ solvesystem (solve_system.jl)
+extern "C" int cgo_solvesys_begin(cgo_state *st) {
+    CGO_CHECK(st != nullptr, "NULL state");
+    cudaStream_t s = st->ctx->stream;
+    if (!st->xn) CGO_CUDA(cudaMalloc(&st->xn, sizeof(double) * (size_t)(st->n + 4)));
+    CGO_CUDA(cudaMemsetAsync(st->xn, 0, sizeof(double) * (size_t)(st->n + 4), s));
+    CGO_CUDA(cudaMemcpyAsync(st->xn, st->x, sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToDevice, s));   // :78 x_next = copy(x_initial)
+    return 0;
+}
+extern "C" int cgo_solvesys_project(cgo_state *st, double m, int32_t fix_stale_iterate, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    CGO_CHECK(st->xn != nullptr, "cgo_solvesys_project before cgo_solvesys_begin");
+    SolveSysProject op;
+    op.base = (const double2 *)(fix_stale_iterate ? st->x : st->xn);
+    op.gp = (const double2 *)st->gp; op.xn = (double2 *)st->xn; op.m = m;
+    CGO_TRY(launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx, CGO_PACK_LEN - 1)));
+    // f_x_next = fdf!(info.df_xp, x_next) (:179) through the trial kernels: xp = x_next + 0·u
+    // (exact for finite u), g⁺ = g(x_next), and the whole dot pack against the OLD df_x and u,
+    // which is what getβ (:201-206) reads
+    double *x_saved = st->x;
+    st->x = st->xn;
+    int rc = st->obj->eval_trial(st, 0.0, false, 0.0, out);
+    st->x = x_saved;
+    return rc;
+}
+extern "C" int cgo_solvesys_accept(cgo_state *st, int32_t fix_stale_iterate) {
+    CGO_CHECK(st != nullptr, "NULL state");
+    // x, x_next = x_next, x (:198); df_x[:] = info.df_xp (:209); info.x[:] = x (:210).  xp holds a
+    // copy of x_next (xp = x_next + 0·u), so the ordinary pointer swap adopts it; x_next then has
+    // to hold the OLD x, which only the as-written variant reads again
+    CGO_TRY(cgo_accept(st));
+    if (!fix_stale_iterate)
+        CGO_CUDA(cudaMemcpyAsync(st->xn, st->xp, sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToDevice, st->ctx->stream));
+    return 0;
 }
 
 // ------------------------------------------------------------------ L-BFGS

@@ -166,6 +166,7 @@ struct cgo_state {
     bool peer_x = false;
     std::vector<void *> xpeers[2];   // per allocation (0: base[0]'s, 1: base[3]'s at creation)
     int xp_alloc = 1;                // which of the two allocations is xp right now (flips on accept)
+    double *xn = nullptr;             // solvesystem's x_next (solve_system.jl:78), allocated by cgo_solvesys_begin
     // L-BFGS history
     int m = 0, count = 0, head = 0, staged = -1;
     std::vector<double *> S, Y;

@@ -385,7 +385,38 @@ class DeviceLineSearchContainer:
         check(lib().cgo_lbfgs_update_dir(self.h, dptr(self._buf)))
         self.dpack = self._buf[:2].copy()
 
+    # -- solvesystem (src/engine/solve_system.jl) --------------------------------------
+    def solvesys_begin(self):
+        """x_next = copy(x_initial) (solve_system.jl:82)"""
+        check(lib().cgo_solvesys_begin(self.h))
+
+    def solvesys_project(self, m, fix_stale_iterate=False):
+        """updateiteratesolvesys! (:237-253) + f_x_next = fdf!(info.df_xp, x_next) (:179):
+        returns (f_x_next, norm(info.df_xp)); the pack holds the getβ dots."""
+        self._materialize_direction()
+        self._cached = None
+        check(lib().cgo_solvesys_project(self.h, float(m), int(bool(fix_stale_iterate)), dptr(self._buf)))
+        self.pack = self._buf.copy()
+        self.fdf_evals += 1
+        return f64(self.pack[P_PHI]), np.sqrt(f64(self.pack[P_GPGP]))
+
+    def solvesys_accept(self, fix_stale_iterate=False):
+        """x, x_next = x_next, x; df_x[:] = info.df_xp; info.x[:] = x (:196, :207-208)"""
+        self._cached = None
+        check(lib().cgo_solvesys_accept(self.h, int(bool(fix_stale_iterate))))
+
+    def dot_df_xp_u(self):
+        """dot(df_xp, u) (solve_system.jl:246): reduced by the trial kernel that produced df_xp"""
+        return f64(self.pack[P_DPHI])
+
     # -- results ---------------------------------------------------------------------
+    def download_trial(self):
+        """info.xp, info.df_xp on the host (updateresult! with the container, types.jl:116-131)"""
+        x, g = capi.pinned_empty(self.n), capi.pinned_empty(self.n)
+        check(lib().cgo_download_vector(self.h, 3, dptr(x)))
+        check(lib().cgo_download_vector(self.h, 4, dptr(g)))
+        return x, g
+
     def download(self):
         x, g = capi.pinned_empty(self.n), capi.pinned_empty(self.n)
         check(lib().cgo_download(self.h, dptr(x), dptr(g)))

@@ -73,7 +73,8 @@ enum {
     CGO_ST_A_MAX_OVERFLOW = 6, CGO_ST_LS_MAX_ITERS = 7, CGO_ST_ZOOM_MAX_ITERS = 8,
     CGO_ST_ACCEPTED_NON_FINITE = 9, CGO_ST_NO_INITIAL_FEASIBLE = 10, CGO_ST_MAX_STEP_LENGTH = 11,
     CGO_ST_NO_FEASIBLE_STEP = 12, CGO_ST_NON_FINITE_STEP = 13, CGO_ST_SAME_STEP = 14,
-    CGO_ST_BRACKET_PRECISION = 15
+    CGO_ST_BRACKET_PRECISION = 15, CGO_ST_LINESEARCH_FAILED = 16 /* solve_system.jl:140 */,
+    CGO_ST_INFEASIBLE_START = 17, CGO_ST_CENTERING_STEP_ISSUE = 18 /* primal_barrier.jl:189, :223 */
 };
 
 /* ---------------------------------------------------------------- context ---------------- */
@@ -172,6 +173,17 @@ int cgo_lbfgs_stage_pair(cgo_state *st, double out[CGO_PACK_LEN]);
 int cgo_lbfgs_commit_pair(cgo_state *st, int32_t commit, double rho, double gamma);
 /* two-loop recursion on the device: u = −H g.  out[CGO_D_GU], out[CGO_D_UU]. */
 int cgo_lbfgs_update_dir(cgo_state *st, double out[CGO_PACK_LEN]);
+/* solvesystem (src/engine/solve_system.jl:64-239, CG for nonlinear systems g(x) = 0).  The line
+ * search (:29-55) is cgo_eval_trial; these are its three other vector steps:
+ *  begin    x_next = copy(x) (:82);
+ *  project  updateiteratesolvesys! (:237-253): x_next = base + m·df_xp, then f_x_next = fdf!(df_xp,
+ *           x_next) (:179) with the usual pack (CGO_P_PHI = f(x_next), CGO_P_GPGP = ‖g(x_next)‖², getβ
+ *           dots against the old df_x and u).  base = x_next as the reference writes it (which from
+ *           the 2nd iteration on is the iterate BEFORE x), or x when fix_stale_iterate != 0;
+ *  accept   x, x_next = x_next, x; df_x = df_xp; info.x = x (:196, :207-208). */
+int cgo_solvesys_begin(cgo_state *st);
+int cgo_solvesys_project(cgo_state *st, double m, int32_t fix_stale_iterate, double out[CGO_PACK_LEN]);
+int cgo_solvesys_accept(cgo_state *st, int32_t fix_stale_iterate);
 /* Results.minimizer / Results.gradient (types.jl:107-114): one D2H each; NULL skips */
 int cgo_download(cgo_state *st, double *x_host, double *g_host);
 /* test hook: 0 x, 1 g, 2 u, 3 xp, 4 g⁺ */

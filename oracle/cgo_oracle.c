@@ -95,7 +95,7 @@ void orc_set_cgo_batched(int B) {       /* the batched solver's order: B lanes, 
     g_blas1_U = 8; g_site_V = 2; g_site_U = 8;
 }
 static double cgo_cta_combine(double *lane /* CGO_B, clobbered */) {
-    double wsum[CGO_BMAX / 32];
+    double wsum[CGO_BMAX / 32] = {0};
     for (int w = 0; w < CGO_B / 32; ++w) {
         double *v = lane + 32 * w, t[32];
         for (int off = 16; off >= 1; off >>= 1) {
@@ -1050,6 +1050,130 @@ done:
         for (int k = 0; k < S.hist.m; ++k) { free(S.hist.S[k]); free(S.hist.Y[k]); }
         free(S.hist.S); free(S.hist.Y); free(S.hist.rho); free(S.hist.alpha);
     }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * solvesystem: CG for a nonlinear system g(x) = 0 (Yuan, Wang & Sheng 2019, Alg. 3.1),
+ * src/engine/solve_system.jl.  `fdf!` returns some merit value f and writes g(x) into its first
+ * argument.  Restated with its quirks:
+ *  - linesearch! (:29-55) returns the 0-based trial index i as its "evaluation count" (:50);
+ *  - its failure return (:54) reads the loop variable `i` outside the loop: in Julia that is an
+ *    UndefVarError, so the :linesearch_failed branch of solvesystem (:131-142) is never reached
+ *    by the reference itself.  The evident intent is restated here: status ORC_LINESEARCH_FAILED;
+ *  - updateiteratesolvesys! (:237-253, called at :171-177) adds the projection step to `x_next`, which
+ *    after the first swap (:196) holds the iterate BEFORE the current one, not the current one:
+ *    from the second iteration on the method no longer follows Alg. 3.1 and in practice diverges
+ *    (Booth, dev/solve_sys.jl settings: 1000 iterations to x ≈ (−683, −686)).  This is the
+ *    default (bit-for-bit drop-in); ls->fix_stale_iterate = 1 projects from the current iterate.
+ * a = s·ρ^i uses C pow (Julia's Float64^Int is its own accurate power; the two can differ in the
+ * last place — third-party arithmetic, version unpinned).
+ * ---------------------------------------------------------------------------------------- */
+int orc_solvesystem(orc_objective *obj, const double *x0, const orc_config *cfg,
+                    const orc_solvesys_ls *ls, double *x_out, double *g_out, orc_result *res,
+                    double *tr_f, double *tr_gnorm, double *tr_step, int64_t *tr_evals) {
+    if (!(0.0 < cfg->eps && cfg->eps < 1.0)) return -1;                     /* types.jl:187 */
+    if (!(0.0 < ls->rho && ls->rho < 1.0 && ls->s > 0.0)) return -2;        /* solve_system.jl:21-23 */
+    if (cfg->flavour == ORC_LBFGS) return -3;                               /* BT <: CGβConfig (:69) */
+    int64_t D = obj->n;
+    solver S;
+    memset(&S, 0, sizeof(S));
+    S.obj = obj; S.cfg = cfg;
+    obj->sum_mode = cfg->sum_mode;
+    if (cfg->threads > 0) obj->threads = cfg->threads;
+    double *df_x = vtmp(D), *x = vtmp(D), *x_next = vtmp(D);                /* :80-82 */
+    memcpy(x, x0, sizeof(double) * (size_t)D);
+    memcpy(x_next, x0, sizeof(double) * (size_t)D);
+    S.info.n = D;
+    S.info.xp = vtmp(D); S.info.df_xp = vtmp(D); S.info.x = vtmp(D); S.info.u = vtmp(D);
+    ls_container *I = &S.info;
+    double f_x = obj->fdf(obj, df_x, x);                                    /* :86 */
+    S.evals_total++;
+    double norm_df_x = tnorm(&S, df_x);                                     /* :87 */
+    for (int64_t i = 0; i < D; ++i) I->u[i] = -df_x[i];                     /* :105, cg_flavours.jl:22-35 */
+    memcpy(I->x, x, sizeof(double) * (size_t)D);
+    memcpy(I->xp, x, sizeof(double) * (size_t)D);
+    memcpy(I->df_xp, df_x, sizeof(double) * (size_t)D);
+    int status = ORC_INCOMPLETE;
+    int64_t iters_ran = 0, trace_len = 0, n_it;
+    const double *xr = x, *gr = df_x;                                       /* what updateresult! copies */
+    for (n_it = 1; n_it <= cfg->max_iters; ++n_it) {                        /* :109 */
+        if (norm_df_x < cfg->eps) {                                         /* :112-123 */
+            status = ORC_SUCCESS; iters_ran = trace_len = n_it - 1;
+            goto done;
+        }
+        /* linesearch!, :29-55 */
+        double norm_u_sq = vdot(&S, I->u, I->u);                            /* :39 */
+        double f_xp = 0.0, norm_df_xp = NAN, a_star = NAN;
+        int64_t evals = 0;
+        int ok = 0;
+        for (int64_t i = 0; i < ls->max_iters; ++i) {                       /* :41 */
+            double a = ls->s * pow(ls->rho, (double)i);                     /* :42 */
+            double dphi;
+            eval_phi_dphi(&S, a, &f_xp, &dphi);                             /* :44 */
+            norm_df_xp = tnorm(&S, I->df_xp);                               /* :47 */
+            if (!(-dphi < ls->sigma * a * norm_df_xp * norm_u_sq)) {        /* :48 */
+                a_star = a; evals = i; ok = 1;
+                break;
+            }
+        }
+        if (!ok) {                                                          /* :131-142 */
+            status = ORC_LINESEARCH_FAILED; iters_ran = trace_len = n_it - 1;
+            goto done;
+        }
+        if (norm_df_xp < cfg->eps) {                                        /* :146-168 */
+            status = ORC_SUCCESS; iters_ran = trace_len = n_it;
+            f_x = f_xp; xr = I->xp; gr = I->df_xp;
+            if (tr_f) {
+                tr_f[n_it - 1] = f_xp; tr_gnorm[n_it - 1] = tnorm(&S, I->df_xp);
+                tr_step[n_it - 1] = a_star; tr_evals[n_it - 1] = evals;
+            }
+            goto done;
+        }
+        /* updateiteratesolvesys!, :237-253 (m :246, loop :248-250) */
+        double m = a_star * tdot(&S, I->df_xp, I->u) / (norm_df_xp * norm_df_xp);
+        if (ls->fix_stale_iterate)      /* Alg. 3.1 as published: project from the CURRENT iterate */
+            for (int64_t i = 0; i < D; ++i) x_next[i] = x[i] + m * I->df_xp[i];
+        else                            /* as written (:171-177, :249): x_next still holds the iterate before x */
+            for (int64_t i = 0; i < D; ++i) x_next[i] = x_next[i] + m * I->df_xp[i];
+        double f_x_next = obj->fdf(obj, I->df_xp, x_next);                  /* :179 */
+        S.evals_total++;
+        double nrm_next = tnorm(&S, I->df_xp);
+        if (!isfinite(f_x_next) || !isfinite(nrm_next)) {                   /* :180-194 */
+            status = ORC_NON_FINITE_PROPOSED; iters_ran = trace_len = n_it - 1;
+            goto done;
+        }
+        { double *t = x; x = x_next; x_next = t; }                          /* :196 */
+        xr = x;
+        f_x = f_x_next;
+        double beta = 0.0;                                                  /* :201-206 */
+        switch (cfg->flavour) {
+        case ORC_YWS: beta = beta_hz_family(&S, I->df_xp, df_x, I->u, 1); break;
+        case ORC_SA: beta = beta_sa(&S, I->df_xp, df_x, I->u); break;
+        case ORC_LS: beta = beta_ls(&S, I->df_xp, df_x, I->u); break;
+        default: beta = beta_hz_family(&S, I->df_xp, df_x, I->u, 0); break;
+        }
+        memcpy(df_x, I->df_xp, sizeof(double) * (size_t)D);                 /* :207 */
+        memcpy(I->x, x, sizeof(double) * (size_t)D);                        /* :208 */
+        norm_df_x = nrm_next;                                               /* :209 (same vector, same order) */
+        for (int64_t i = 0; i < D; ++i) I->u[i] = -df_x[i] + beta * I->u[i];   /* :212 */
+        if (tr_f) {                                                         /* :215-222 */
+            tr_f[n_it - 1] = f_x; tr_gnorm[n_it - 1] = norm_df_x;
+            tr_step[n_it - 1] = a_star; tr_evals[n_it - 1] = evals;
+        }
+    }
+    status = ORC_MAX_ITERS_REACHED;                                         /* :225-233 */
+    iters_ran = trace_len = cfg->max_iters;
+done:
+    res->objective = f_x;
+    res->iters_ran = iters_ran;
+    res->status = status;
+    res->trace_len = trace_len;
+    res->fdf_evals_total = S.evals_total;
+    memcpy(x_out, xr, sizeof(double) * (size_t)D);
+    memcpy(g_out, gr, sizeof(double) * (size_t)D);
+    free(df_x); free(x); free(x_next);
+    free(I->xp); free(I->df_xp); free(I->x); free(I->u);
     return 0;
 }
 

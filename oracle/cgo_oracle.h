@@ -39,7 +39,11 @@ enum {
     ORC_NO_FEASIBLE_STEP = 12,          /* wolfe.jl:157 */
     ORC_NON_FINITE_STEP = 13,           /* geometric.jl:129 */
     ORC_SAME_STEP = 14,                 /* geometric.jl:133 */
-    ORC_BRACKET_PRECISION = 15          /* wolfe.jl:131 (unreachable: missing `return`) */
+    ORC_BRACKET_PRECISION = 15,         /* wolfe.jl:131 (unreachable: missing `return`) */
+    ORC_LINESEARCH_FAILED = 16,         /* solve_system.jl:140 */
+    /* primalbarriermethod!, primal_barrier.jl:189, 223, 250 (plus ORC_SUCCESS, ORC_MAX_ITERS_REACHED) */
+    ORC_INFEASIBLE_START = 17,
+    ORC_CENTERING_STEP_ISSUE = 18
 };
 
 enum { ORC_HZ = 0, ORC_YWS = 1, ORC_SA = 2, ORC_LS = 3, ORC_LBFGS = 4 };
@@ -130,6 +134,18 @@ void orc_rosenbrock_x0(int64_t n, uint64_t seed, double perturb, double *x0);
 int orc_minimize(orc_objective *obj, const double *x0, const orc_config *cfg, double *x_out,
                  double *g_out, orc_result *res, double *tr_f, double *tr_gnorm, double *tr_step,
                  int64_t *tr_evals);
+
+/* LinesearchSolveSys, src/engine/solve_system.jl:7-12 */
+typedef struct {
+    double rho, sigma, s;
+    int64_t max_iters;
+    int32_t fix_stale_iterate;  /* 0: as written (solve_system.jl:172,251); 1: Alg. 3.1 of Yuan et al. as published */
+    int32_t _pad;
+} orc_solvesys_ls;
+/* engine: solvesystem (src/engine/solve_system.jl:64-239) */
+int orc_solvesystem(orc_objective *obj, const double *x0, const orc_config *cfg,
+                    const orc_solvesys_ls *ls, double *x_out, double *g_out, orc_result *res,
+                    double *tr_f, double *tr_gnorm, double *tr_step, int64_t *tr_evals);
 
 /* engine: minimizeobjectivererun (optim.jl:173-208).  cfgs[0] is the primary config, cfgs[1..]
  * the backups.  res/x_out/g_out/trace arrays are laid out attempt-major with stride

@@ -21,7 +21,7 @@ STATUS = [
     "linesearch_a_max_overflow", "linesearch_max_iters_reached", "zoom_max_iters_reached",
     "accepted_non_finite_iterate", "cannot_find_initial_feasible_step", "max_step_length_reached",
     "cannot_find_feasible_step", "non_finite_step_proposed", "proposed_step_same_as_current_step",
-    "step_bracket_precision_issue",
+    "step_bracket_precision_issue", "linesearch_failed", "infeasible_start", "centering_step_issue",
 ]
 FLAVOURS = {"HagerZhang": 0, "YuanWangSheng": 1, "SallehAlhawarat": 2, "LiuStorrey": 3, "LBFGS": 4}
 LS_KINDS = {"StrongWolfeBisection": 0, "Wolfe": 1, "YuanWeiLuWolfe": 2, "Backtracking": 3}
@@ -302,6 +302,46 @@ def minimize(obj: Objective, x0, cfg: OrcConfig, trace=True) -> OracleResult:
                         _dp(tf) if trace else None, _dp(tg) if trace else None,
                         _dp(ta) if trace else None,
                         te.ctypes.data_as(C.POINTER(C.c_int64)) if trace else None)
+    if rc != 0:
+        raise AssertionError(f"oracle config assertion failed (rc={rc})")
+    k = res.trace_len if trace else 0
+    return OracleResult(res.objective, xo, go, res.iters_ran, STATUS[res.status], tf[:k].copy(),
+                        tg[:k].copy(), ta[:k].copy(), te[:k].copy(), res.fdf_evals_total)
+
+
+class OrcSolveSysLS(C.Structure):
+    """LinesearchSolveSys, src/engine/solve_system.jl:7-12"""
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("s", C.c_double), ("max_iters", C.c_int64),
+                ("fix_stale_iterate", C.c_int32), ("_pad", C.c_int32)]
+
+
+def solvesys_ls(s, sigma=0.5, rho=0.95, max_iters=None, fix_stale_iterate=False) -> OrcSolveSysLS:
+    """setupLinesearchSolveSys (solve_system.jl:14-26); default max_iters = round(log(ρ, 1e-6))"""
+    import math
+    if max_iters is None:
+        max_iters = round(math.log(1e-6) / math.log(rho))
+    return OrcSolveSysLS(rho, sigma, s, int(max_iters), int(bool(fix_stale_iterate)), 0)
+
+
+def solvesystem(obj: Objective, x0, cfg: OrcConfig, ls: OrcSolveSysLS, trace=True) -> OracleResult:
+    """solvesystem, src/engine/solve_system.jl:64-239."""
+    L = lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = obj.n
+    assert x0.size == n
+    xo, go = np.empty(n), np.empty(n)
+    res = OrcResult()
+    mi = max(int(cfg.max_iters), 1)
+    tf, tg, ta = np.zeros(mi), np.zeros(mi), np.zeros(mi)
+    te = np.zeros(mi, dtype=np.int64)
+    L.orc_solvesystem.restype = C.c_int
+    L.orc_solvesystem.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(OrcConfig), C.POINTER(OrcSolveSysLS),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(OrcResult),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int64)]
+    rc = L.orc_solvesystem(obj.h, _dp(x0), C.byref(cfg), C.byref(ls), _dp(xo), _dp(go), C.byref(res),
+                           _dp(tf) if trace else None, _dp(tg) if trace else None, _dp(ta) if trace else None,
+                           te.ctypes.data_as(C.POINTER(C.c_int64)) if trace else None)
     if rc != 0:
         raise AssertionError(f"oracle config assertion failed (rc={rc})")
     k = res.trace_len if trace else 0

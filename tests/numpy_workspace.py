@@ -120,6 +120,31 @@ class NumpyWorkspace:
     def norm_df_xp(self):
         return np.sqrt(f64(self.pack[P_GPGP]))
 
+    # solvesystem (src/engine/solve_system.jl): same call shapes as DeviceLineSearchContainer
+    def solvesys_begin(self):
+        self.xn_ = self.x_.copy()
+
+    def solvesys_project(self, m, fix_stale_iterate=False):
+        self._mat()
+        base = self.x_ if fix_stale_iterate else self.xn_
+        with np.errstate(all="ignore"):
+            self.xn_ = base + float(m) * self.gp_
+        x_saved, self.x_ = self.x_, self.xn_
+        f, _ = self.eval_trial(0.0)          # xp = x_next + 0·u, like the device path
+        self.x_ = x_saved
+        return f, self.norm_df_xp()
+
+    def solvesys_accept(self, fix_stale_iterate=False):
+        self.accept()
+        if not fix_stale_iterate:
+            self.xn_ = self.xp_.copy()       # the old x
+
+    def dot_df_xp_u(self):
+        return f64(self.pack[P_DPHI])
+
+    def download_trial(self):
+        return self.xp_.copy(), self.gp_.copy()
+
     def beta_literal(self, R, m):
         with np.errstate(all="ignore"):
             y = self.gp_ - self.g_
