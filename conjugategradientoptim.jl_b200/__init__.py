@@ -15,10 +15,12 @@ from .qn_flavours import LBFGS  # noqa: F401
 from .cg_utils import evalϕdϕ_  # noqa: F401
 from .linesearch import (Armijo, Backtracking, StrongWolfeBisection, Wolfe, WolfeBisection,  # noqa: F401
                          YuanWeiLuWolfe, setupStrongWolfeBisection)
-from .engine import (LinesearchSolveSys, MinimizerRun, minimizeobjective, minimizeobjectivererun,  # noqa: F401
-                     setupLinesearchSolveSys, solvesystem)
+from .engine import (BoxConstraint, CvxInequalityConstraint, LinesearchSolveSys, MinimizerRun,  # noqa: F401
+                     PrimalBarrierConfig, PrimalBarrierResults, getNconstraints, minimizeobjective,
+                     minimizeobjectivererun, primalbarriermethod_, setupCvxInequalityConstraint,
+                     setupLinesearchSolveSys, setupPrimalBarrierConfig, solvesystem, verifyt0)
 from .engine.optim import linesearch_  # noqa: F401
 from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceVector,  # noqa: F401
-                     LogRegGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,
+                     BoxBarrierGPU, LogRegGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,
                      dot, shard_range, BatchedResults, minimizeobjective_batched, batched_lanes)
 from .device import DeviceLineSearchContainer as LineSearchContainer  # noqa: F401

@@ -60,6 +60,9 @@ _SIGS = {
     "cgo_obj_sparse_ls_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(_vp)]),
     "cgo_obj_sparse_ls_create_csr": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "cgo_obj_logreg_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.POINTER(_vp)]),
+    "cgo_obj_box_barrier_create": (C.c_int, [_vp, _vp, _dp, _dp, C.c_double, C.POINTER(_vp)]),
+    "cgo_obj_barrier_set_t": (C.c_int, [_vp, C.c_double]),
+    "cgo_obj_barrier_infeasible": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "cgo_obj_destroy": (C.c_int, [_vp]),
     "cgo_obj_dims": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cgo_obj_bytes_per_eval": (C.c_int, [_vp, _dp]),

@@ -494,6 +494,154 @@ extern "C" int cgo_obj_default_x0(cgo_obj *o, uint64_t seed, double perturb, dou
     return o->default_x0(seed, perturb, x0);
 }
 
+// ------------------------------------------------------------------ box-constraint log barrier
+// evalbarrier! (src/engine/primal_barrier.jl:112-133) with the box constraints of
+// examples/constrained.jl:17-47 (fi = [x − ubs; lbs − x], dfi = [+e_d; −e_d]) around any device
+// objective: the inner objective's trial kernels leave xp and g⁺ = ∇f0(xp); this BLAS-1 pass
+// forms df = t·∇f0 + dψ in place (:130), ψ = −Σ log(−fi) after clamp!(fi, −Inf, 0) (:77-78), and —
+// because g⁺ changed — every dot of the trial pack again (cg_utils.jl:20, optim.jl:107, getβ).
+struct BarrierFinish {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 9;
+    static constexpr int OCC = 2;
+    struct In { double2 xp, gp, u, g, lo, hi; };
+    const double2 *xp, *u, *g, *lo, *hi;
+    double2 *gp;
+    double t;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.xp = cgo_ld2(xp + q); r.gp = ld2rw(gp + q); r.u = cgo_ld2(u + q); r.g = cgo_ld2(g + q);
+        r.lo = cgo_ld2(lo + q); r.hi = cgo_ld2(hi + q);
+        return r;
+    }
+    __device__ __forceinline__ void one(double x, double g0, double uu, double gg, double lb, double ub, double &gn,
+                                        double (&acc)[K]) const {
+        double fu = x - ub, fl = lb - x;
+        if (fu > 0.0) fu = 0.0;                      // clamp!(fi_evals, -Inf, 0): NaN stays NaN
+        if (fl > 0.0) fl = 0.0;
+        const double term = log(-fu) + log(-fl);
+        double dpsi = 0.0 - 1.0 / fu;                // dψ[d] -= dfi[i][d]/fi[i], upper then lower (:80-85)
+        dpsi = dpsi - (-1.0) / fl;
+        gn = t * g0 + dpsi;                          // :130
+        const double y = gn - gg;
+        acc[CGO_P_PHI] = acc[CGO_P_PHI] + term;
+        acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn * uu;
+        acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn * gn;
+        acc[CGO_P_YY] = acc[CGO_P_YY] + y * y;
+        acc[CGO_P_UY] = acc[CGO_P_UY] + uu * y;
+        acc[CGO_P_YGP] = acc[CGO_P_YGP] + y * gn;
+        acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn * gg;
+        acc[CGO_P_UG] = acc[CGO_P_UG] + uu * gg;
+        acc[CGO_P_UU] = acc[CGO_P_UU] + uu * uu;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 gn;
+        one(in.xp.x, in.gp.x, in.u.x, in.g.x, in.lo.x, in.hi.x, gn.x, acc);
+        if (v2) one(in.xp.y, in.gp.y, in.u.y, in.g.y, in.lo.y, in.hi.y, gn.y, acc);
+        else gn.y = 0.0;
+        cgo_st2(gp + q, gn);
+    }
+};
+// any(fi_evals .>= 0) (primal_barrier.jl:189): number of coordinates on or outside the box
+struct BoxInfeasible {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 4;
+    struct In { double2 x, lo, hi; };
+    const double2 *x, *lo, *hi;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.x = cgo_ld2(x + q); r.lo = cgo_ld2(lo + q); r.hi = cgo_ld2(hi + q);
+        return r;
+    }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        if (in.x.x - in.hi.x >= 0.0 || in.lo.x - in.x.x >= 0.0) acc[0] = acc[0] + 1.0;
+        if (v2 && (in.x.y - in.hi.y >= 0.0 || in.lo.y - in.x.y >= 0.0)) acc[0] = acc[0] + 1.0;
+    }
+};
+
+struct BarrierObj : cgo_obj {
+    cgo_obj *inner = nullptr;
+    double *lo = nullptr, *hi = nullptr;
+    double t = 1.0;
+    ~BarrierObj() override {
+        if (ctx) cudaSetDevice(ctx->device);
+        cudaFree(lo); cudaFree(hi);
+    }
+    int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        double in[CGO_PACK_LEN];
+        CGO_TRY(inner->eval_trial(st, a, fused, beta, in));      // xp, g⁺ = ∇f0(xp), f0, direction dots
+        BarrierFinish op;
+        op.xp = (const double2 *)st->xp; op.gp = (double2 *)st->gp; op.u = (const double2 *)st->u;
+        op.g = (const double2 *)st->g; op.lo = (const double2 *)lo; op.hi = (const double2 *)hi; op.t = t;
+        CGO_TRY(launch_blas1(ctx, op, st->n, cgo_red_args(ctx)));
+        CGO_TRY(cgo_finish_pack(ctx, 9, out));
+        out[CGO_P_PHI] = t * in[CGO_P_PHI] + (-out[CGO_P_PHI]);   // :132  t*f_x + ψ_x
+        out[CGO_P_DIR_GU] = in[CGO_P_DIR_GU];
+        out[CGO_P_DIR_UU] = in[CGO_P_DIR_UU];
+        out[CGO_P_XPXP] = in[CGO_P_XPXP];
+        return 0;
+    }
+    double bytes_per_eval() const override { return inner->bytes_per_eval() + 8.0 * 7.0 * (double)n_local; }
+    int default_x0(uint64_t seed, double perturb, double *x0) override { return inner->default_x0(seed, perturb, x0); }
+};
+
+extern "C" int cgo_obj_box_barrier_create(cgo_ctx *ctx, cgo_obj *inner, const double *lbs, const double *ubs,
+                                          double t, cgo_obj **out) {
+    CGO_CHECK(ctx && inner && lbs && ubs && out, "NULL argument");
+    CGO_CHECK(inner->ctx == ctx, "inner objective belongs to another ctx");
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    BarrierObj *o = new BarrierObj();
+    o->ctx = ctx; o->inner = inner; o->t = t;
+    o->n_global = inner->n_global; o->n_local = inner->n_local; o->offset = inner->offset;
+    o->halo = inner->halo; o->n_alloc = inner->n_alloc;
+    const size_t len = (size_t)(o->n_local + 4);
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&o->lo, sizeof(double) * len));
+        CGO_CUDA(cudaMalloc(&o->hi, sizeof(double) * len));
+        CGO_CUDA(cudaMemsetAsync(o->lo, 0, sizeof(double) * len, ctx->stream));
+        CGO_CUDA(cudaMemsetAsync(o->hi, 0, sizeof(double) * len, ctx->stream));
+        CGO_CUDA(cudaMemcpyAsync(o->lo, lbs, sizeof(double) * (size_t)o->n_local, cudaMemcpyHostToDevice, ctx->stream));
+        CGO_CUDA(cudaMemcpyAsync(o->hi, ubs, sizeof(double) * (size_t)o->n_local, cudaMemcpyHostToDevice, ctx->stream));
+        CGO_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    int rc = body();
+    if (rc) { delete o; return rc; }
+    *out = o;
+    return 0;
+}
+extern "C" int cgo_obj_barrier_set_t(cgo_obj *obj, double t) {
+    BarrierObj *o = dynamic_cast<BarrierObj *>(obj);
+    CGO_CHECK(o != nullptr, "not a barrier objective");
+    o->t = t;
+    return 0;
+}
+extern "C" int cgo_obj_barrier_infeasible(cgo_obj *obj, const double *x_host, int64_t *count) {
+    BarrierObj *o = dynamic_cast<BarrierObj *>(obj);
+    CGO_CHECK(o && x_host && count, "not a barrier objective / NULL argument");
+    cgo_ctx *c = o->ctx;
+    CGO_CUDA(cudaSetDevice(c->device));
+    double *dx = nullptr;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&dx, sizeof(double) * (size_t)(o->n_local + 4)));
+        CGO_CUDA(cudaMemsetAsync(dx, 0, sizeof(double) * (size_t)(o->n_local + 4), c->stream));
+        CGO_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * (size_t)o->n_local, cudaMemcpyHostToDevice, c->stream));
+        BoxInfeasible op;
+        op.x = (const double2 *)dx; op.lo = (const double2 *)o->lo; op.hi = (const double2 *)o->hi;
+        CGO_TRY(launch_blas1(c, op, o->n_local, cgo_red_args(c)));
+        double v[CGO_PACK_LEN];
+        CGO_TRY(cgo_finish_pack(c, 1, v));
+        *count = (int64_t)v[0];
+        return 0;
+    };
+    int rc = body();
+    cudaFree(dx);
+    return rc;
+}
+
 // ------------------------------------------------------------------ solver state
 static int alloc_vec(cgo_state *st, double **base, double **ptr) {
     size_t len = (size_t)(st->n + 2 * st->halo + 4);

@@ -234,6 +234,33 @@ def LogRegGPU(nsamples: int, nfeat: int, nnz_per_row: int = 20, seed: int = 24, 
     return DeviceObjective(ctx, h)
 
 
+class BoxBarrierGPU(DeviceObjective):
+    """t·f0(x) − Σ log(ubs − x) − Σ log(x − lbs) around a device objective: the `fdf!` closure that
+    primalbarriermethod! builds (src/engine/primal_barrier.jl:205-213, evalbarrier! :112-133) for the
+    box constraints of examples/constrained.jl:17-47.  lbs / ubs are this rank's shard."""
+
+    def __init__(self, inner: DeviceObjective, lbs, ubs, t: float = 1.0):
+        lbs = np.ascontiguousarray(lbs, dtype=np.float64)
+        ubs = np.ascontiguousarray(ubs, dtype=np.float64)
+        if lbs.shape != (inner.n_local,) or ubs.shape != (inner.n_local,):
+            raise ValueError("lbs / ubs must have the objective's (local) dimension")
+        h = C.c_void_p()
+        check(lib().cgo_obj_box_barrier_create(inner.ctx.h, inner.h, dptr(lbs), dptr(ubs), float(t), C.byref(h)))
+        super().__init__(inner.ctx, h)
+        self.inner, self.lbs, self.ubs, self.t = inner, lbs, ubs, float(t)
+
+    def set_t(self, t: float):
+        check(lib().cgo_obj_barrier_set_t(self.h, float(t)))
+        self.t = float(t)
+
+    def infeasible_count(self, x) -> int:
+        """how many coordinates (over all ranks) have x − ub >= 0 or lb − x >= 0 (primal_barrier.jl:189)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = C.c_int64()
+        check(lib().cgo_obj_barrier_infeasible(self.h, dptr(x), C.byref(v)))
+        return v.value
+
+
 # ---------------------------------------------------------------------------------- vectors
 class DeviceVector:
     """Token for one of the device-resident vectors of a LineSearchContainer."""

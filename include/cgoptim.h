@@ -131,6 +131,15 @@ int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t ncols, con
 int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t nsamples, int64_t nfeat,
                                     int32_t nnz_per_row, uint64_t seed, double lambda,
                                     cgo_obj **out);
+/* t·f0(x) − Σ log(ubs − x) − Σ log(x − lbs) around `inner` (which must outlive it): evalbarrier!
+ * (src/engine/primal_barrier.jl:112-133) with the box constraints of examples/constrained.jl:17-47;
+ * lbs / ubs are this rank's shard.  cgo_obj_barrier_set_t changes t between centering steps (:246);
+ * cgo_obj_barrier_infeasible counts the coordinates of x (host, this rank's shard; all ranks' counts
+ * are added) with fi >= 0, the feasibility test of :187-198. */
+int cgo_obj_box_barrier_create(cgo_ctx *ctx, cgo_obj *inner, const double *lbs_host, const double *ubs_host,
+                               double t, cgo_obj **out);
+int cgo_obj_barrier_set_t(cgo_obj *obj, double t);
+int cgo_obj_barrier_infeasible(cgo_obj *obj, const double *x_host, int64_t *count);
 int cgo_obj_destroy(cgo_obj *obj);
 int cgo_obj_dims(cgo_obj *obj, int64_t *n_local, int64_t *n_global, int64_t *offset);
 int cgo_obj_bytes_per_eval(cgo_obj *obj, double *bytes);   /* algorithmic HBM bytes of one fdf! on this rank */

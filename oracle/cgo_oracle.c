@@ -242,6 +242,10 @@ struct orc_objective {
     double lambda;
     int owns;
     int trial_V, trial_U;   /* canonical-order mapping of this objective's trial kernels */
+    /* box-constraint log barrier around another objective (primal_barrier.jl) */
+    orc_objective *inner;
+    double *lbs, *ubs;
+    double t;
 };
 
 /* Booth, examples/helpers/test_funcs.jl:3-12 */
@@ -367,6 +371,48 @@ static double logreg_fdf(orc_objective *o, double *g, const double *w) {
     return loss + (0.5 * o->lambda) * ww;
 }
 
+/* evalbarrier! (src/engine/primal_barrier.jl:112-133) with the box constraints of
+ * examples/constrained.jl:17-47: fi = [x − ubs; lbs − x], dfi = [+e_d; −e_d].
+ *   f0 = fdf!(df_x, x)                                                     :121
+ *   evalconstraints! (:63-91): clamp!(fi, −Inf, 0) (:77); ψ = −Σ log(−fi) (:78);
+ *     dψ[d] −= dfi[i][d]/fi[i] over all constraints (:80-85): for a box, dψ[d] = (0 − 1/fu_d) − (−1/fl_d)
+ *     (the other terms subtract ±0).  Not restated: with fi[i] = 0 (a point on or outside the box) the
+ *     reference's dense loop makes EVERY entry of dψ NaN (0/0); here only entry d is non-finite.
+ *     Either way ‖g‖ and g·u are non-finite and ϕ = +Inf, which is all the line searches test.
+ *   df_x = t .* df_x .+ dψ (:130);  return t*f0 + ψ (:132)
+ * ORC_SUM_CGO: ψ's 2n log terms are added element by element (upper, lower) by the BLAS-1
+ * barrier kernel (V = 2, U = 4); otherwise in the reference's order (all uppers, then all lowers). */
+static double box_barrier_fdf(orc_objective *o, double *g, const double *x) {
+    orc_objective *in = o->inner;
+    int64_t n = o->n;
+    in->sum_mode = o->sum_mode; in->threads = o->threads;
+    double f0 = in->fdf(in, g, x);
+    double *tu = o->scratch2, *tl = o->scratch;
+    for (int64_t d = 0; d < n; ++d) {
+        double fu = x[d] - o->ubs[d], fl = o->lbs[d] - x[d];
+        if (fu > 0.0) fu = 0.0;             /* clamp!(fi_evals, -Inf, 0): NaN stays NaN */
+        if (fl > 0.0) fl = 0.0;
+        tu[d] = log(-fu);
+        tl[d] = log(-fl);
+        double dpsi = 0.0 - 1.0 / fu;
+        dpsi = dpsi - (-1.0) / fl;
+        g[d] = o->t * g[d] + dpsi;
+    }
+    double sum;
+    if (o->sum_mode == ORC_SUM_CGO) {
+        for (int64_t d = 0; d < n; ++d) tu[d] = tu[d] + tl[d];
+        int sv = g_site_V, su = g_site_U;
+        g_site_V = 2; g_site_U = g_blas1_U;
+        sum = cgo_reduce(sum_term, tu, n, 2, g_blas1_U, 2);
+        g_site_V = sv; g_site_U = su;
+    } else {
+        sum = 0.0;
+        for (int64_t d = 0; d < n; ++d) sum += tu[d];
+        for (int64_t d = 0; d < n; ++d) sum += tl[d];
+    }
+    return o->t * f0 + (-sum);
+}
+
 static orc_objective *obj_new(int64_t n, fdf_fn f) {
     orc_objective *o = (orc_objective *)calloc(1, sizeof(*o));
     o->n = n; o->fdf = f; o->sum_mode = ORC_SUM_SEQ; o->threads = 1;
@@ -379,6 +425,19 @@ orc_objective *orc_obj_rosenbrock(int64_t n) { return (n % 2) ? NULL : obj_new(n
 orc_objective *orc_obj_rosenbrock_chained(int64_t n) { return obj_new(n, rosen_chained_fdf); }
 orc_objective *orc_obj_quartic_barrier(int64_t n) { return obj_new(n, barrier_fdf); }
 int64_t orc_obj_dim(const orc_objective *o) { return o->n; }
+/* the inner objective stays owned by the caller and must outlive the barrier objective */
+orc_objective *orc_obj_box_barrier(orc_objective *inner, const double *lbs, const double *ubs, double t) {
+    orc_objective *o = obj_new(inner->n, box_barrier_fdf);
+    o->inner = inner; o->t = t; o->owns = 1;
+    o->lbs = (double *)malloc(sizeof(double) * (size_t)inner->n);
+    o->ubs = (double *)malloc(sizeof(double) * (size_t)inner->n);
+    o->scratch = (double *)malloc(sizeof(double) * (size_t)inner->n);
+    memcpy(o->lbs, lbs, sizeof(double) * (size_t)inner->n);
+    memcpy(o->ubs, ubs, sizeof(double) * (size_t)inner->n);
+    o->trial_V = 2; o->trial_U = 4;     /* the barrier kernel (BLAS-1) reduces the trial's dots */
+    return o;
+}
+void orc_obj_barrier_set_t(orc_objective *o, double t) { o->t = t; }
 void orc_obj_set_sum_mode(orc_objective *o, int mode, int threads) { o->sum_mode = mode; if (threads > 0) o->threads = threads; }
 void orc_obj_trial_site(const orc_objective *o, int *V, int *U) { *V = o->trial_V; *U = o->trial_U; }
 
@@ -520,6 +579,7 @@ void orc_obj_destroy(orc_objective *o) {
     free(o->rowptr); free(o->col); free(o->val);
     free(o->rowptrT); free(o->colT); free(o->valT);
     free(o->b); free(o->scratch); free(o->scratch2); free(o->scratch2rows);
+    free(o->lbs); free(o->ubs);
     free(o);
 }
 int64_t orc_csr_nnz(const orc_objective *o) { return o->nnz; }

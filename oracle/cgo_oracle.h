@@ -100,6 +100,10 @@ orc_objective *orc_obj_sparse_ls_csr(int64_t nrows, int64_t ncols, const int64_t
                                      int32_t threads);
 orc_objective *orc_obj_logreg_synth(int64_t nsamples, int64_t nfeat, int32_t nnz_per_row,
                                     uint64_t seed, double lambda, int32_t threads);
+/* box-constraint log barrier t·f0(x) − Σ log(ubs − x) − Σ log(x − lbs) around `inner`
+ * (evalbarrier!, src/engine/primal_barrier.jl:112-133 with examples/constrained.jl:17-47's box) */
+orc_objective *orc_obj_box_barrier(orc_objective *inner, const double *lbs, const double *ubs, double t);
+void orc_obj_barrier_set_t(orc_objective *, double t);
 void orc_obj_destroy(orc_objective *);
 int64_t orc_obj_dim(const orc_objective *);
 void orc_obj_set_sum_mode(orc_objective *, int sum_mode, int threads);

@@ -23,6 +23,7 @@ STATUS = [
     "cannot_find_feasible_step", "non_finite_step_proposed", "proposed_step_same_as_current_step",
     "step_bracket_precision_issue", "linesearch_failed", "infeasible_start", "centering_step_issue",
 ]
+SUM_NAMES = {0: "seq", 1: "pairwise", 2: "comp", 3: "cgo"}
 FLAVOURS = {"HagerZhang": 0, "YuanWangSheng": 1, "SallehAlhawarat": 2, "LiuStorrey": 3, "LBFGS": 4}
 LS_KINDS = {"StrongWolfeBisection": 0, "Wolfe": 1, "YuanWeiLuWolfe": 2, "Backtracking": 3}
 SUM_MODES = {"seq": 0, "pairwise": 1, "comp": 2, "cgo": 3}
@@ -74,6 +75,9 @@ def lib():
     L.orc_obj_sparse_ls_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.orc_obj_logreg_synth.restype = C.c_void_p
     L.orc_obj_logreg_synth.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_int32]
+    L.orc_obj_box_barrier.restype = C.c_void_p
+    L.orc_obj_box_barrier.argtypes = [C.c_void_p, dp, dp, C.c_double]
+    L.orc_obj_barrier_set_t.argtypes = [C.c_void_p, C.c_double]
     L.orc_obj_destroy.argtypes = [C.c_void_p]
     L.orc_obj_dim.restype = C.c_int64
     L.orc_obj_dim.argtypes = [C.c_void_p]
@@ -180,6 +184,21 @@ class Objective:
     @staticmethod
     def barrier(n):
         return Objective(lib().orc_obj_quartic_barrier(n))
+
+    @staticmethod
+    def box_barrier(inner: "Objective", lbs, ubs, t=1.0):
+        """t·f0 − Σ log(ubs − x) − Σ log(x − lbs): evalbarrier! (primal_barrier.jl:112-133) with the
+        box constraints of examples/constrained.jl:17-47"""
+        lbs = np.ascontiguousarray(lbs, dtype=np.float64)
+        ubs = np.ascontiguousarray(ubs, dtype=np.float64)
+        assert lbs.size == inner.n == ubs.size
+        o = Objective(lib().orc_obj_box_barrier(inner.h, _dp(lbs), _dp(ubs), float(t)))
+        o.inner, o.lbs, o.ubs, o.t = inner, lbs, ubs, float(t)      # keeps the inner objective alive
+        return o
+
+    def set_t(self, t):
+        lib().orc_obj_barrier_set_t(self.h, float(t))
+        self.t = float(t)
 
     @staticmethod
     def sparse_ls(n, nnz_per_row=10, W=None, seed=24, coh_log2=0, threads=1):
@@ -371,3 +390,49 @@ def minimize_rerun(obj: Objective, x0, cfgs) -> list[OracleResult]:
                                 STATUS[res[i].status], tf[i, :t].copy(), tg[i, :t].copy(),
                                 ta[i, :t].copy(), te[i, :t].copy(), res[i].fdf_evals_total))
     return out
+
+
+# ---------------------------------------------------------------------------------- primal barrier
+@dataclass
+class OraclePrimalBarrierResults:
+    """PrimalBarrierResults, src/engine/primal_barrier.jl:1-7"""
+    centering_results: list
+    status: str
+    iters_ran: int
+    t_final: float
+    total_objective_evals: int
+
+
+def primalbarrier(f0: Objective, lbs, ubs, x0, cfgs, barrier_tol, barrier_growth_factor, max_iters,
+                  t_initial=float("nan"), update_iterate=False) -> OraclePrimalBarrierResults:
+    """primalbarriermethod! (src/engine/primal_barrier.jl:158-255, Alg. 11.1 of Boyd 2004) for box
+    constraints; cfgs[0] is the centering config, cfgs[1:] the rerun backups.  As written, every
+    centering step starts from x_initial (`x` is never updated inside the loop, :215-247); update_iterate=True
+    (not in the reference) continues from the previous centre as Alg. 11.1 does."""
+    lbs, ubs = np.asarray(lbs, dtype=np.float64), np.asarray(ubs, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64)
+    n_constraints = 2 * x.size                                                  # :176
+    rets = []
+
+    def assemble(status, it, t):                                                # :9-34
+        total = sum(int(r.trace_objective_evals.sum()) for step in rets[:it] for r in step)
+        return OraclePrimalBarrierResults(rets[:it], status, it, t, total)
+
+    if np.any(x - ubs >= 0.0) or np.any(lbs - x >= 0.0):                        # :187-198
+        return assemble("infeasible_start", 0, t_initial)
+    t = float(t_initial)                                                        # :200, verifyt0 :259-277
+    if not np.isfinite(t) or t < 0.0:
+        f0.set_sum_mode(SUM_NAMES[cfgs[0].sum_mode])
+        t = (f0.fdf(x)[0] - 0.0) * barrier_growth_factor
+    bar = Objective.box_barrier(f0, lbs, ubs, t)
+    for i in range(1, max_iters + 1):                                           # :215
+        bar.set_t(t)
+        rets.append(minimize_rerun(bar, x, cfgs))                               # :217-223
+        if rets[-1][-1].status != "success":                                    # :224-232
+            return assemble("centering_step_issue", i, t)
+        if n_constraints / t < barrier_tol:                                     # :235-243
+            return assemble("success", i, t)
+        if update_iterate:
+            x = rets[-1][-1].minimizer.copy()
+        t = barrier_growth_factor * t                                           # :246
+    return assemble("max_iters_reached", max_iters, t)                          # :249-254

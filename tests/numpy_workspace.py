@@ -30,6 +30,24 @@ class NumpyObjective:
         return NumpyWorkspace(self, x_initial, lbfgs_m, fuse_direction, beta_form)
 
 
+class NumpyBoxBarrier(NumpyObjective):
+    """numpy stand-in of BoxBarrierGPU (the oracle's box_barrier objective)"""
+
+    def __init__(self, f0: NumpyObjective, lbs, ubs, t=1.0):
+        self.f0, self.lbs, self.ubs = f0, np.asarray(lbs, dtype=np.float64), np.asarray(ubs, dtype=np.float64)
+        super().__init__(O.Objective.box_barrier(f0.o, self.lbs, self.ubs, t), f0.sum_mode)
+
+    def set_t(self, t):
+        self.o.set_t(t)
+
+    def infeasible_count(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return int(np.sum((x - self.ubs >= 0.0) | (self.lbs - x >= 0.0)))
+
+    def close(self):
+        pass
+
+
 class NumpyWorkspace:
     def __init__(self, obj, x_initial, lbfgs_m, fuse_direction, beta_form):
         self.obj, self.o = obj, obj.o
