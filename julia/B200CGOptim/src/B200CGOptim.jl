@@ -22,12 +22,14 @@ import ConjugateGradientOptim: CGConfig, Results, TraceContainer, EnableTrace, D
     minimizeobjective, minimizeobjectivererun, linesearch!, evalϕdϕ!, getβ, updatedir!,
     initializeβ, initializeLineSearchContainer!, evalwolfeconditions, evalbacktrackcondition
 
-export Context, RosenbrockGPU, SparseLSGPU, LogRegGPU, LBFGS, DeviceObjective
+export Context, RosenbrockGPU, SparseLSGPU, LogRegGPU, LBFGS, DeviceObjective,
+    BoxConstraint, BoxBarrierGPU, BatchedConfig, minimizeobjective_batched
 
 include("capi.jl")
 include("device.jl")
 include("flavours.jl")
 include("linesearch.jl")
 include("optim.jl")
+include("extras.jl")     # solvesystem, primalbarriermethod!, batched solver
 
 end # module
