@@ -227,3 +227,59 @@ def test_statuses_reachable(linesearch):
         # (Backtracking adopts the REJECTED trial with the previous ϕ, geometric.jl:141-144 →
         # optim.jl:136-139, SURVEY.md §8a LS-3: it can step outside the feasible box; replicated)
         assert np.all(np.abs(r.minimizer) < 1.0)
+
+
+# ------------------------------------------------------------------ golden traces of the callers
+CALLERS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "traces_callers.json")
+
+
+def _caller_cases(kind):
+    with open(CALLERS) as f:
+        return [c for c in json.load(f)["cases"] if c["kind"] == kind]
+
+
+@pytest.mark.parametrize("idx", range(16))
+def test_oracle_reproduces_golden_solvesystem(idx):
+    """solvesystem (src/engine/solve_system.jl) on dev/solve_sys.jl's settings, as written and with
+    fix_stale_iterate (tests/golden/traces_callers.json, restatement-derived)."""
+    c = _caller_cases("solvesystem")[idx]
+    cfg = O.make_config(c["flavour"], max_iters=c["max_iters"], sum_mode=c["sum_mode"], beta_form=c["beta_form"], mu=0.1)
+    r = O.solvesystem(O.Objective.booth(), np.array([0.43, 1.23]), cfg,
+                      O.solvesys_ls(1.0, fix_stale_iterate=c["fix_stale_iterate"]))
+    k = len(c["trace_objective"])
+    assert r.status == c["status"] and r.iters_ran == c["iters_ran"] and r.fdf_evals_total == c["fdf_evals_total"]
+    assert [int(v) for v in r.trace_objective_evals[:k]] == c["trace_objective_evals"]
+    assert np.array_equal(r.trace_objective[:k], _unhex(c["trace_objective"]))
+    assert np.array_equal(r.trace_grad_norm[:k], _unhex(c["trace_grad_norm"]))
+    assert np.array_equal(r.trace_step_size[:k], _unhex(c["trace_step_size"]))
+    assert np.array_equal(r.minimizer, _unhex(c["minimizer"]))
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_oracle_reproduces_golden_primal_barrier(idx):
+    """primalbarriermethod! on examples/constrained.jl's problem (log terms: libm, so the scalar
+    outcomes are pinned exactly and the objectives to 1e-9)."""
+    c = _caller_cases("primalbarrier")[idx]
+    cfgs = [O.make_config("HagerZhang", "Wolfe", c1=1e-3, c2=0.9, ls_max_iters=100, sum_mode="cgo", beta_form="fused"),
+            O.make_config("LiuStorrey", "Backtracking", c1=1e-3, c2=0.9, ls_max_iters=300, sum_mode="cgo", beta_form="fused")]
+    b = O.primalbarrier(O.Objective.booth(), [-10.0, -10.0], [10.0, 10.0], [0.43, 1.23], cfgs, 1e-8, 10.0, 100,
+                        update_iterate=c["update_iterate"])
+    assert b.status == c["status"] and b.iters_ran == c["iters_ran"] and b.t_final == float.fromhex(c["t_final"])
+    assert [len(s) for s in b.centering_results] == c["attempts"]
+    assert [s[-1].status for s in b.centering_results] == c["final_statuses"]
+    np.testing.assert_allclose([s[-1].objective for s in b.centering_results], _unhex(c["final_objectives"]), rtol=1e-9)
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_oracle_reproduces_golden_batched_order(idx):
+    """the batched solver's reduction order (32 lanes, one tile: oracle.set_cgo_batched)"""
+    c = _caller_cases("batched_order")[idx]
+    ocfg, _, _ = make_pair("HagerZhang", c["linesearch"], max_iters=200)
+    O.set_cgo_batched(c["lanes"])
+    try:
+        r = O.minimize(O.Objective.rosenbrock(512), O.rosenbrock_x0(512, 24, 0.1), ocfg)
+    finally:
+        O.set_cgo_lanes(256)
+    assert r.status == c["status"] and r.iters_ran == c["iters_ran"] and r.fdf_evals_total == c["fdf_evals_total"]
+    assert r.objective == float.fromhex(c["objective"])
+    assert np.array_equal(r.trace_objective[:len(c["trace_objective"])], _unhex(c["trace_objective"]))
