@@ -473,6 +473,18 @@ extern "C" int cgo_obj_rosenbrock_create(cgo_ctx *ctx, int64_t n_global, cgo_obj
     *out = o;
     return 0;
 }
+int cgo_obj::hessvec_dir(cgo_state *, double *) {
+    cgo_set_error("this objective has no Hessian-vector product (CSR least squares has)");
+    return 2;
+}
+extern "C" int cgo_hessvec_dir(cgo_state *st, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    if (!st->hv) {
+        CGO_CUDA(cudaMalloc(&st->hv, sizeof(double) * (size_t)(st->n + 4)));
+        CGO_CUDA(cudaMemsetAsync(st->hv, 0, sizeof(double) * (size_t)(st->n + 4), st->ctx->stream));
+    }
+    return st->obj->hessvec_dir(st, out);
+}
 extern "C" int cgo_obj_destroy(cgo_obj *o) {
     delete o;
     return 0;
@@ -668,6 +680,7 @@ extern "C" int cgo_state_destroy(cgo_state *st) {
     for (auto p : st->Y) cudaFree(p);
     cudaFree(st->q);
     cudaFree(st->xn);
+    cudaFree(st->hv);
     delete st;
     return 0;
 }
@@ -960,8 +973,8 @@ extern "C" int cgo_download(cgo_state *st, double *x_host, double *g_host) {
 }
 extern "C" int cgo_download_vector(cgo_state *st, int32_t which, double *host) {
     CGO_CHECK(st && host, "NULL argument");
-    double *src[5] = {st->x, st->g, st->u, st->xp, st->gp};
-    CGO_CHECK(which >= 0 && which < 5, "which=%d out of range", which);
+    double *src[6] = {st->x, st->g, st->u, st->xp, st->gp, st->hv};
+    CGO_CHECK(which >= 0 && which < 6 && src[which] != nullptr, "which=%d out of range (5 = hv needs cgo_hessvec_dir first)", which);
     CGO_CUDA(cudaMemcpyAsync(host, src[which], sizeof(double) * (size_t)st->n, cudaMemcpyDeviceToHost, st->ctx->stream));
     CGO_CUDA(cudaStreamSynchronize(st->ctx->stream));
     return 0;

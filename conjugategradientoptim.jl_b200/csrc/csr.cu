@@ -129,6 +129,20 @@ __device__ __forceinline__ double ld_gather_f64(const double *p, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
     return r;
 }
+// predicated gather: a lane whose row has ended issues no request at all.  (A gather instruction
+// costs one L1TEX wavefront per distinct 128-byte line; re-reading a dummy address on the idle
+// lanes — the first version — spent half of the gather bandwidth of the 5-entry rows of a
+// column-block pass on nothing.)
+__device__ __forceinline__ double ld_gather_f64_if(const double *p, uint64_t pol, bool on) {
+    double r = 0.0;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %3, 0;\n"
+        "@q ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;\n"
+        "}\n" : "+d"(r) : "l"(p), "l"(pol), "r"((int)on));
+    return r;
+}
 
 template <class Epi>
 __global__ void __launch_bounds__(TS_THREADS, TS_OCC)
@@ -255,7 +269,7 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
                 const int hi = (int)((re < ce ? re : ce) - cs);
                 for (int k0 = lo; k0 < hi; k0 += TS_UN) {
                     // branch-free batch: TS_UN gathers are issued back to back (entries past the
-                    // row's end re-read its last entry and are not added)
+                    // row's end are predicated off and not added)
                     double vj[TS_UN], xj[TS_UN];
 #pragma unroll
                     for (int j = 0; j < TS_UN; ++j) {
@@ -263,7 +277,7 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
                         uint32_t idx = head + (uint32_t)kk;
                         if (idx >= RING) idx -= RING;
                         vj[j] = s_val[idx];
-                        xj[j] = ld_gather_f64(xg + s_col[idx], gpol);
+                        xj[j] = ld_gather_f64_if(xg + s_col[idx], gpol, k0 + j < hi);
                     }
 #pragma unroll
                     for (int j = 0; j < TS_UN; ++j) {
@@ -416,6 +430,37 @@ struct EpiPushPart {
         while (o > 0 && j < flo[o]) --o;
         while (o + 1 < nranks && j >= flo[o + 1]) ++o;
         ((double *)recv_all[o])[j - flo[o]] = sum;
+    }
+};
+
+// Hessian-vector product of least squares, ∇²f u = Aᵀ(A u): v = A u with Σ v² (= u·Hu), then
+// hv = Aᵀ v with u·hv and hv·hv
+struct EpiStoreSq {
+    static constexpr int K = 1, NOPS = 0;
+    static constexpr bool HAS_INIT = false;
+    struct Pre {};
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
+    double *y;
+    __device__ __forceinline__ const double *operand(int) const { return nullptr; }
+    __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
+    __device__ __forceinline__ void row(int64_t i, double sum, const Pre &, double (&acc)[K]) const {
+        y[i] = sum;
+        acc[0] = acc[0] + sum * sum;
+    }
+};
+struct EpiHv {
+    static constexpr int K = 2, NOPS = 1;
+    static constexpr bool HAS_INIT = false;
+    struct Pre { double u; };
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
+    double *hv;
+    const double *u;
+    __device__ __forceinline__ const double *operand(int) const { return u; }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const { return Pre{ops[t]}; }
+    __device__ __forceinline__ void row(int64_t j, double sum, const Pre &p, double (&acc)[K]) const {
+        hv[j] = sum;
+        acc[0] = acc[0] + p.u * sum;
+        acc[1] = acc[1] + sum * sum;
     }
 };
 
@@ -934,6 +979,18 @@ struct CsrObj : cgo_obj {
     int exchange(double *v, int64_t nloc) {
         if (halo == 0) return 0;
         return cgo_sendrecv_ring(ctx, v, v + nloc, v + nloc - halo, v - halo, halo);
+    }
+    // ∇²f u = Aᵀ(A u) along the current direction (north_star's Hessian-vector product; the reference
+    // engine never calls one, src/engine/optim.jl:83-145).  `r` is scratch between trials.
+    int hessvec_dir(cgo_state *st, double *out) override {
+        CGO_CHECK(!logreg, "the Hessian-vector product is implemented for least squares");
+        CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
+        EpiStoreSq e1{r};
+        CGO_TRY(launch_csr(ctx, A, st->u, e1, cgo_red_args(ctx, 0), CGO_T_SPMV));
+        CGO_TRY(exchange(r, nrows));
+        EpiHv e2{st->hv, st->u};
+        CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, 1), CGO_T_SPMVT));
+        return cgo_finish_pack(ctx, 3, out);
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
         if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);

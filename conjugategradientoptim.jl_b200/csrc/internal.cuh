@@ -150,6 +150,9 @@ struct cgo_obj {
     // finishes it into out_host.
     virtual int eval_trial(cgo_state *st, double a, bool fused_dir, double beta,
                            double *out_host) = 0;
+    // Hessian-vector product along the current direction: hv = ∇²f(x) u; out[0] = u·Hu (as ‖Au‖² for
+    // least squares), out[1] = u·hv, out[2] = hv·hv.  Objectives without one return an error.
+    virtual int hessvec_dir(cgo_state *st, double *out_host);
     virtual double bytes_per_eval() const = 0;
     virtual int default_x0(uint64_t seed, double perturb, double *x0_host) = 0;
 };
@@ -166,6 +169,7 @@ struct cgo_state {
     bool peer_x = false;
     std::vector<void *> xpeers[2];   // per allocation (0: base[0]'s, 1: base[3]'s at creation)
     int xp_alloc = 1;                // which of the two allocations is xp right now (flips on accept)
+    double *hv = nullptr;             // Hessian-vector product scratch (cgo_hessvec_dir), allocated on first use
     double *xn = nullptr;             // solvesystem's x_next (solve_system.jl:78), allocated by cgo_solvesys_begin
     // L-BFGS history
     int m = 0, count = 0, head = 0, staged = -1;

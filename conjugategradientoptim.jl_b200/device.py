@@ -412,6 +412,17 @@ class DeviceLineSearchContainer:
         check(lib().cgo_lbfgs_update_dir(self.h, dptr(self._buf)))
         self.dpack = self._buf[:2].copy()
 
+    # -- curvature ------------------------------------------------------------------
+    def hessvec_dir(self):
+        """∇²f(x) u along the current direction (CSR least squares: Aᵀ(A u)) -> (u·Hu, hv on the host).
+        u·Hu is what an exact line minimisation of a quadratic needs: a* = −(g·u)/(u·Hu)."""
+        self._materialize_direction()
+        check(lib().cgo_hessvec_dir(self.h, dptr(self._buf)))
+        uHu = f64(self._buf[0])
+        hv = np.empty(self.n)
+        check(lib().cgo_download_vector(self.h, 5, dptr(hv)))
+        return uHu, hv
+
     # -- solvesystem (src/engine/solve_system.jl) --------------------------------------
     def solvesys_begin(self):
         """x_next = copy(x_initial) (solve_system.jl:82)"""

@@ -193,9 +193,14 @@ int cgo_lbfgs_update_dir(cgo_state *st, double out[CGO_PACK_LEN]);
 int cgo_solvesys_begin(cgo_state *st);
 int cgo_solvesys_project(cgo_state *st, double m, int32_t fix_stale_iterate, double out[CGO_PACK_LEN]);
 int cgo_solvesys_accept(cgo_state *st, int32_t fix_stale_iterate);
+/* Hessian-vector product along the current direction, hv = ∇²f(x) u (CSR least squares: Aᵀ(A u), two
+ * SpMV launches; the curvature a quadratic-aware line search needs — the reference engine itself
+ * never forms one, src/engine/optim.jl:83-145).  out[0] = u·Hu (as ‖Au‖²), out[1] = u·hv, out[2] = hv·hv;
+ * hv is readable with cgo_download_vector(st, 5, …). */
+int cgo_hessvec_dir(cgo_state *st, double out[CGO_PACK_LEN]);
 /* Results.minimizer / Results.gradient (types.jl:107-114): one D2H each; NULL skips */
 int cgo_download(cgo_state *st, double *x_host, double *g_host);
-/* test hook: 0 x, 1 g, 2 u, 3 xp, 4 g⁺ */
+/* test hook: 0 x, 1 g, 2 u, 3 xp, 4 g⁺, 5 hv */
 int cgo_download_vector(cgo_state *st, int32_t which, double *host);
 
 /* ---------------------------------------------------------------- batched solver ----------

@@ -222,3 +222,33 @@ def test_large_n_properties(ctx, n):
     assert np.all(np.diff(r1.trace.objective) < 0)
     assert np.array_equal(r1.trace.objective, r2.trace.objective) and np.array_equal(r1.minimizer, r2.minimizer)
     obj.close()
+
+
+def test_hessian_vector_product_and_exact_line_minimum(ctx):
+    """north_star's Hessian-vector product of the least-squares objective: hv = Aᵀ(A u) through the
+    production SpMV kernels, against scipy; and what it is for — on a quadratic,
+    ϕ(α) = ϕ₀ + α dϕ₀ + ½ α² u·Hu, so a* = −dϕ₀ / u·Hu zeroes the directional derivative."""
+    import scipy.sparse as sp
+    n = 30_000
+    obj = cg.SparseLSGPU(n, 10, 512, 24, 0, ctx)
+    rp, ci, va, b = obj.csr(False)
+    A = sp.csr_matrix((va, ci, rp), shape=(n, n))
+    x0 = np.random.default_rng(5).standard_normal(n)
+    ws = obj.make_workspace(x0, fuse_direction=False)
+    ws.reset_direction()                                   # u = −g
+    g = ws.download()[1]
+    uHu, hv = ws.hessvec_dir()
+    ref = A.T @ (A @ (-g))
+    np.testing.assert_allclose(hv, ref, rtol=1e-12, atol=1e-12 * np.max(np.abs(ref)))
+    assert abs(uHu - (-g) @ ref) <= 1e-12 * abs(uHu)
+    dphi0 = ws.dot_g_u()
+    a_star = -dphi0 / uHu
+    phi, dphi = ws.eval_trial(a_star)
+    assert abs(dphi) <= 1e-9 * abs(dphi0)                  # exact minimiser along u
+    assert abs(phi - (ws.f_x0 + a_star * dphi0 + 0.5 * a_star**2 * uHu)) <= 1e-11 * abs(ws.f_x0)
+    ws.close()
+    ro = cg.RosenbrockGPU(64, ctx)                         # objectives without one say so
+    w2 = ro.make_workspace(np.zeros(64))
+    with pytest.raises(cg.CgoError):
+        w2.hessvec_dir()
+    w2.close(); ro.close(); obj.close()
