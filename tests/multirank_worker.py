@@ -57,6 +57,40 @@ def main():
             obj = cg.SparseLSGPU(n, 10, 2048, 24, coh, ctx)
             check(f"sparse_ls coh={coh}", obj, np.zeros(n), O.Objective.sparse_ls(n, 10, 2048, 24, coh), flavour, 60)
             obj.close()
+    # the callers next to the hot path, sharded: solvesystem (src/engine/solve_system.jl) bit for bit,
+    # the box log barrier (src/engine/primal_barrier.jl) at the libm tolerance
+    n = 40_000
+    for fix in (False, True):
+        ocfg, cfg, _ = make_pair("YuanWangSheng", max_iters=8 if not fix else 20)
+        obj = cg.SparseLSGPU(n, 10, 2048, 24, 0, ctx)
+        lo, hi = obj.offset, obj.offset + obj.n_local
+        ret = cg.solvesystem(obj, np.zeros(hi - lo), cfg, cg.setupLinesearchSolveSys(1.0), fix_stale_iterate=fix)
+        ora = O.solvesystem(O.Objective.sparse_ls(n, 10, 2048, 24, 0), np.zeros(n), ocfg,
+                            O.solvesys_ls(1.0, fix_stale_iterate=fix))
+        ok = (ret.status == ora.status and ret.iters_ran == ora.iters_ran
+              and np.array_equal(ret.trace.objective, ora.trace_objective)
+              and np.array_equal(ret.trace.grad_norm, ora.trace_grad_norm)
+              and np.array_equal(ret.trace.objective_evals, ora.trace_objective_evals)
+              and np.array_equal(ret.minimizer, ora.minimizer[lo:hi]))
+        if not ok:
+            fails.append(f"solvesystem fix={fix}: rank {rank} {ret.status}/{ora.status} {ret.iters_ran}/{ora.iters_ran}")
+        obj.close()
+    lbs, ubs = -2.0 * np.ones(n), 0.8 * np.ones(n)
+    ocfg, cfg, ls = make_pair("HagerZhang", max_iters=30, eps=1e-6)
+    f0 = cg.RosenbrockGPU(n, ctx)
+    lo, hi = f0.offset, f0.offset + f0.n_local
+    bar = cg.BoxBarrierGPU(f0, lbs[lo:hi], ubs[lo:hi], 5.0)
+    assert bar.infeasible_count(np.zeros(hi - lo)) == 0 and bar.infeasible_count(np.ones(hi - lo)) == n
+    ret = cg.minimizeobjective(bar, np.zeros(hi - lo), cfg, ls)
+    ora = O.minimize(O.Objective.box_barrier(O.Objective.rosenbrock(n), lbs, ubs, 5.0), np.zeros(n), ocfg)
+    k = min(25, len(ora.trace_objective), len(ret.trace.objective))
+    ok = (k >= 5 and np.array_equal(ret.trace.step_size[:k], ora.trace_step_size[:k])
+          and np.allclose(ret.trace.objective[:k], ora.trace_objective[:k], rtol=1e-10, atol=0)
+          and np.allclose(ret.minimizer, ora.minimizer[lo:hi], rtol=1e-7, atol=1e-9))
+    if not ok:
+        fails.append(f"barrier: rank {rank} {ret.status}/{ora.status} {ret.iters_ran}/{ora.iters_ran} k={k}")
+    bar.close(); f0.close()
+
     # cfg 4 (BASELINE.json configs[3]): sample-sharded logistic regression + L-BFGS.  exp / log1p
     # differ from glibc in the last ulp and the gradient partials are added shard by shard, so the
     # comparison is at north_star's tolerances with identical line-search decisions.
