@@ -48,6 +48,8 @@ def parse():
                    help="sparse_ls generator: log2 of the number of consecutive rows sharing their column "
                         "offsets (30: ten true diagonals, SURVEY.md §8d cfg 3; 0: independent offsets per row)")
     p.add_argument("--reduction-ctas", type=int, default=0, help="canonical-order G (0: library default)")
+    p.add_argument("--quadratic-ls", action="store_true",
+                   help="sparse_ls only: the quadratic-aware line search (SURVEY.md §8f N1), one SpMV + one SpMVT per iteration")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -293,7 +295,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # polling runs through the warm-up; only the timed window is reported
-    run = cg.MinimizerRun(obj, x0, cfg, ls)
+    qkw = {"quadratic_linesearch": True} if (args.quadratic_ls and args.workload == "sparse_ls") else {}
+    run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
     for _ in range(W):
         assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
     ctx.timing(True)
@@ -331,7 +334,7 @@ def run_ours(args):
             assert run.ret.iters_ran > 0, f"restarted run made no progress: {run.ret.status}"
             life = run.ret.iters_ran if life is None else min(life, run.ret.iters_ran)
             run.info.close()
-            run = cg.MinimizerRun(obj, x0, cfg, ls)
+            run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
             restarts += 1
     sampler.mark_end()
     barrier()
@@ -385,14 +388,14 @@ def run_ours(args):
         # one untimed call first: page-locks the result buffers (they are pooled and reused) and
         # warms the allocator, as a long-running host would have done
         cfg1, ls1 = solver_configs(cg, 1, args.workload)
-        cg.minimizeobjective(obj, x0p, cfg1, ls1)
+        cg.minimizeobjective(obj, x0p, cfg1, ls1, **qkw)
         remaining, dt, ev2, calls = K, 0.0, 0, 0
         while remaining > 0:                                 # more than one call only if a run hits the FP64 floor
             per_call = remaining if life is None else max(1, min(remaining, life - 3))
             cfg2, ls2 = solver_configs(cg, per_call, args.workload)
             barrier()
             t0 = time.perf_counter()
-            ret = cg.minimizeobjective(obj, x0p, cfg2, ls2)  # H2D x0 … iterations … D2H x, g
+            ret = cg.minimizeobjective(obj, x0p, cfg2, ls2, **qkw)  # H2D x0 … iterations … D2H x, g
             barrier()
             dt += time.perf_counter() - t0
             assert ret.iters_ran > 0, (ret.iters_ran, ret.status)
@@ -430,7 +433,8 @@ def run_ours(args):
                                     f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
                        "n": n, "sharding": f"rows/vector slices over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (vectors are 8n bytes >> 126 MB)",
-                       "fdf_evals_in_timed_region": evals, "restarts_in_timed_region": restarts, "host": "python/ctypes over the C ABI"},
+                       "fdf_evals_in_timed_region": evals, "restarts_in_timed_region": restarts,
+                       "quadratic_aware_linesearch": bool(qkw), "host": "python/ctypes over the C ABI"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "host_wall_ms_per_step": round(wall_ms / K, 4),
             "objective_trace_head": [float(v) for v in trace_f[:4]],

@@ -87,6 +87,8 @@ _SIGS = {
     "cgo_solvesys_project": (C.c_int, [_vp, C.c_double, C.c_int32, _dp]),
     "cgo_solvesys_accept": (C.c_int, [_vp, C.c_int32]),
     "cgo_hessvec_dir": (C.c_int, [_vp, _dp]),
+    "cgo_quad_begin": (C.c_int, [_vp, _dp]),
+    "cgo_quad_accept": (C.c_int, [_vp, C.c_double, _dp]),
     "cgo_download": (C.c_int, [_vp, _dp, _dp]),
     "cgo_download_vector": (C.c_int, [_vp, C.c_int32, _dp]),
     "cgo_batched_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

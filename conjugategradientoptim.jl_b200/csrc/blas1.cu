@@ -477,6 +477,51 @@ int cgo_obj::hessvec_dir(cgo_state *, double *) {
     cgo_set_error("this objective has no Hessian-vector product (CSR least squares has)");
     return 2;
 }
+int cgo_obj::quad_begin(cgo_state *, double *) {
+    cgo_set_error("this objective has no quadratic-aware line search (CSR least squares has)");
+    return 2;
+}
+int cgo_obj::quad_accept(cgo_state *, double, double *) {
+    cgo_set_error("this objective has no quadratic-aware line search (CSR least squares has)");
+    return 2;
+}
+extern "C" int cgo_quad_begin(cgo_state *st, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    return st->obj->quad_begin(st, out);
+}
+extern "C" int cgo_quad_accept(cgo_state *st, double a, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(st && out, "NULL argument");
+    return st->obj->quad_accept(st, a, out);
+}
+// r = r + a v, Σ r²  (the residual of the accepted step of a quadratic-aware line search)
+struct ResidualAxpy {
+    static constexpr int TCLASS = CGO_T_AXPY;
+    static constexpr int K = 1;
+    static constexpr int OCC = 4;
+    struct In { double2 r, v; };
+    double2 *r;
+    const double2 *v;
+    double a;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In o;
+        o.r = ld2rw(r + q); o.v = cgo_ld2(v + q);
+        return o;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 o;
+        o.x = in.r.x + a * in.v.x;
+        o.y = v2 ? in.r.y + a * in.v.y : 0.0;
+        cgo_st2(r + q, o);
+        acc[0] = acc[0] + o.x * o.x;
+        if (v2) acc[0] = acc[0] + o.y * o.y;
+    }
+};
+int cgo_blas1_residual_axpy(cgo_ctx *c, double *r, const double *v, double a, int64_t nrows, int slot) {
+    ResidualAxpy op;
+    op.r = (double2 *)r; op.v = (const double2 *)v; op.a = a;
+    return launch_blas1(c, op, nrows, cgo_red_args(c, slot));
+}
 extern "C" int cgo_hessvec_dir(cgo_state *st, double out[CGO_PACK_LEN]) {
     CGO_CHECK(st && out, "NULL argument");
     if (!st->hv) {

@@ -464,6 +464,24 @@ struct EpiHv {
     }
 };
 
+// quadratic-aware line search: v = A u with r·v, v·v and r·r (r = residual at x)
+struct EpiQuadV {
+    static constexpr int K = 3, NOPS = 1;
+    static constexpr bool HAS_INIT = false;
+    struct Pre { double r; };
+    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
+    double *v;
+    const double *r;
+    __device__ __forceinline__ const double *operand(int) const { return r; }
+    __device__ __forceinline__ Pre load(const double *ops, int t) const { return Pre{ops[t]}; }
+    __device__ __forceinline__ void row(int64_t i, double sum, const Pre &p, double (&acc)[K]) const {
+        v[i] = sum;
+        acc[0] = acc[0] + p.r * sum;
+        acc[1] = acc[1] + sum * sum;
+        acc[2] = acc[2] + p.r * p.r;
+    }
+};
+
 // Column-blocked matrices (CsrBlocked below): pass j > 0 of a row continues the sum pass j − 1
 // left in `partial` (one more staged operand), so the products of a row are still added one by one
 // in storage order — bit-identical to the single-pass kernel.
@@ -890,6 +908,7 @@ struct CsrObj : cgo_obj {
     int64_t nrows = 0;                 // local rows of A (residuals / samples)
     double *b = nullptr;               // rhs (LS) or labels (logreg), nrows
     double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
+    double *qv = nullptr;                     // v = A u of the quadratic-aware line search (nrows)
     std::vector<void *> rpeers;               // peer mappings of r_base (sharded LS with peer memory)
     bool r_is_peer = false;
     double lambda = 0.0;
@@ -918,7 +937,7 @@ struct CsrObj : cgo_obj {
             cgo_peer_free(ctx, g_recv, grecv_peers, true); g_recv = nullptr;
         }
         cudaFree(d_xpf_dst); cudaFree(d_grecv_dst); cudaFree(d_flo);
-        cudaFree(b); cudaFree(r_base);
+        cudaFree(b); cudaFree(r_base); cudaFree(qv);
         cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
     }
     int alloc_r() {
@@ -991,6 +1010,30 @@ struct CsrObj : cgo_obj {
         EpiHv e2{st->hv, st->u};
         CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, 1), CGO_T_SPMVT));
         return cgo_finish_pack(ctx, 3, out);
+    }
+    // SURVEY.md §8f N1.  `r` must hold the residual at x: true after state creation and after every
+    // accepted step whose last trial was the accepted one (strong-Wolfe / Wolfe searches).
+    int quad_begin(cgo_state *st, double *out) override {
+        CGO_CHECK(!logreg, "the quadratic-aware line search is for least squares");
+        if (!qv) {
+            CGO_CUDA(cudaMalloc(&qv, sizeof(double) * (size_t)(nrows + CSR_PAD)));
+            CGO_CUDA(cudaMemsetAsync(qv, 0, sizeof(double) * (size_t)(nrows + CSR_PAD), ctx->stream));
+        }
+        CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
+        EpiQuadV e1{qv, r};
+        CGO_TRY(launch_csr(ctx, A, st->u, e1, cgo_red_args(ctx, 0), CGO_T_SPMV));
+        return cgo_finish_pack(ctx, 3, out);
+    }
+    int quad_accept(cgo_state *st, double a, double *out) override {
+        CGO_CHECK(!logreg && qv != nullptr, "cgo_quad_accept before cgo_quad_begin");
+        CGO_TRY(cgo_blas1_axpy_dir(st, a, false, 0.0));                                   // xp = x + a u
+        CGO_TRY(cgo_blas1_residual_axpy(ctx, r, qv, a, nrows, CGO_P_PHI));                // r += a v, Σ r²
+        CGO_TRY(exchange(r, nrows));
+        EpiGrad<false> e2{st->gp, st->g, st->u, nullptr, 0.0, 0.0};
+        CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT));  // K_c
+        CGO_TRY(cgo_finish_pack(ctx, 12, out));
+        out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
+        return 0;
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
         if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);

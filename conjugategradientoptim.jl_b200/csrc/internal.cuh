@@ -153,6 +153,12 @@ struct cgo_obj {
     // Hessian-vector product along the current direction: hv = ∇²f(x) u; out[0] = u·Hu (as ‖Au‖² for
     // least squares), out[1] = u·hv, out[2] = hv·hv.  Objectives without one return an error.
     virtual int hessvec_dir(cgo_state *st, double *out_host);
+    // quadratic-aware line search: for f = ½‖Ax − b‖², r(x + a u) = r + a·Au, so
+    // ϕ(a) = ½(r·r) + a (r·v) + ½ a² (v·v) and dϕ(a) = r·v + a (v·v) with v = A u: every trial of one line
+    // search is scalar arithmetic after ONE SpMV.  quad_begin: v = A u, out = {r·v, v·v, r·r};
+    // quad_accept: xp = x + a u, r += a v, g⁺ = Aᵀ r and the usual pack (CGO_P_PHI = ½ Σ r²).
+    virtual int quad_begin(cgo_state *st, double *out_host);
+    virtual int quad_accept(cgo_state *st, double a, double *out_host);
     virtual double bytes_per_eval() const = 0;
     virtual int default_x0(uint64_t seed, double perturb, double *x0_host) = 0;
 };
@@ -194,6 +200,7 @@ struct HaloPush {
     void *const *dst_all = nullptr;
 };
 int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, const HaloPush *push = nullptr);
+int cgo_blas1_residual_axpy(cgo_ctx *ctx, double *r, const double *v, double a, int64_t nrows, int slot);
 // sample-sharded logistic regression: g⁺ = (Σ_r q[r·stride + i]) / N + λ xp, partial gradients
 // added in rank order, fused with the dot pack of EpiGrad (slots CGO_P_DPHI .. CGO_P_UU)
 // wait_epoch != 0: spin until every rank's CGO_F_GPART flag reached it before reading q

@@ -151,8 +151,8 @@ class DeviceObjective:
         return x0
 
     def make_workspace(self, x_initial, lbfgs_m: int = 0, fuse_direction: bool = True,
-                       beta_form: str = "fused"):
-        return DeviceLineSearchContainer(self, x_initial, lbfgs_m, fuse_direction, beta_form)
+                       beta_form: str = "fused", quadratic_linesearch: bool = False):
+        return DeviceLineSearchContainer(self, x_initial, lbfgs_m, fuse_direction, beta_form, quadratic_linesearch)
 
     # CSR test hooks
     def csr(self, transposed=False):
@@ -293,8 +293,15 @@ class DeviceLineSearchContainer:
     """
 
     def __init__(self, objective: DeviceObjective, x_initial, lbfgs_m=0, fuse_direction=True,
-                 beta_form="fused"):
+                 beta_form="fused", quadratic_linesearch=False):
         assert beta_form in ("fused", "literal")
+        # SURVEY.md §8f N1 (CSR least squares only): the trials of a line search are evaluated from
+        # r·v, v·v with v = A u (one SpMV per line search); the accepted step is materialised once
+        self.quadratic = bool(quadratic_linesearch)
+        self._q = None                        # (r·v, v·v, ½ r·r) of the current line search
+        self._q_a = None                      # last trial step, not yet materialised
+        if self.quadratic:
+            fuse_direction = False            # there is no trial kernel for the direction update to ride on
         x0 = np.ascontiguousarray(x_initial, dtype=np.float64)
         if x0.shape != (objective.n_local,):
             raise ValueError(f"x_initial has shape {x0.shape}, objective shard has n={objective.n_local}")
@@ -322,6 +329,7 @@ class DeviceLineSearchContainer:
         """u = −df_x (cg_flavours.jl:28, wolfe.jl:129)."""
         self._pending_beta = None
         self._cached = None
+        self._q = None
         check(lib().cgo_reset_direction(self.h, dptr(self._buf)))
         self.dpack = self._buf[:2].copy()
 
@@ -329,6 +337,7 @@ class DeviceLineSearchContainer:
         """updatedir! (cg_flavours.jl:2-15).  With fuse_direction the kernel is deferred and
         fused into the first trial of the next line search."""
         self._cached = None
+        self._q = None
         if self.fuse_direction:
             self._pending_beta = float(β)
         else:
@@ -370,10 +379,28 @@ class DeviceLineSearchContainer:
         return np.sqrt(f64(v.value))
 
     # -- trial point -----------------------------------------------------------------
+    def _quad_materialize(self):
+        """the accepted step of a quadratic-aware line search: xp, r, g⁺ and the dot pack"""
+        if self._q_a is not None:
+            a, self._q_a = self._q_a, None
+            check(lib().cgo_quad_accept(self.h, a, dptr(self._buf)))
+            self.pack = self._buf.copy()
+            self._q = None
+
     def eval_trial(self, a):
         """evalϕdϕ! (cg_utils.jl:3-22): returns (ϕ, dϕ); the full pack stays in self.pack."""
         self._materialize_direction()
         a = float(a)
+        if self.quadratic:
+            if self._q is None:               # first trial of this line search: v = A u
+                check(lib().cgo_quad_begin(self.h, dptr(self._buf)))
+                self._q = (f64(self._buf[0]), f64(self._buf[1]), f64(0.5) * f64(self._buf[2]))
+            rv, vv, f0 = self._q
+            a64 = f64(a)
+            self._q_a = a
+            self.fdf_evals += 1
+            with np.errstate(all="ignore"):
+                return f0 + a64 * rv + f64(0.5) * a64 * a64 * vv, rv + a64 * vv
         if self._cached is not None and self._cached[0] == a:
             self.pack = self._cached[1]
             self._cached = None
@@ -386,6 +413,7 @@ class DeviceLineSearchContainer:
 
     def norm_df_xp(self):
         """norm(info.df_xp) (optim.jl:107)"""
+        self._quad_materialize()
         return np.sqrt(f64(self.pack[P_GPGP]))
 
     def beta_literal(self, R, m):
@@ -396,6 +424,7 @@ class DeviceLineSearchContainer:
     def accept(self):
         """x[:] = info.xp; df_x[:] = info.df_xp; info.x[:] = x  (optim.jl:136-140): pointer swaps."""
         self._cached = None
+        self._quad_materialize()
         check(lib().cgo_accept(self.h))
 
     # -- L-BFGS ----------------------------------------------------------------------
@@ -409,6 +438,7 @@ class DeviceLineSearchContainer:
     def lbfgs_update_dir(self):
         self._cached = None
         self._pending_beta = None
+        self._q = None
         check(lib().cgo_lbfgs_update_dir(self.h, dptr(self._buf)))
         self.dpack = self._buf[:2].copy()
 

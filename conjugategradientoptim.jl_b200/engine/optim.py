@@ -23,6 +23,7 @@ from ..cg_types import (CGConfig, LineSearchConfig, Results, resizetrace_, setup
                         updateresult_, updatetrace_, βConfig)
 from ..linesearch import geometric, nocedal, wolfe
 from ..qn_flavours import LBFGS
+from .._capi import P_PHI
 
 f64 = np.float64
 
@@ -44,7 +45,7 @@ class MinimizerRun:
     individual iterations; `minimizeobjective` just drives it to completion)."""
 
     def __init__(self, fdf_, x_initial, config: CGConfig, linesearch_config: LineSearchConfig,
-                 fuse_direction: bool = True, beta_form: str = "fused"):
+                 fuse_direction: bool = True, beta_form: str = "fused", quadratic_linesearch: bool = False):
         if not hasattr(fdf_, "make_workspace"):
             raise TypeError(
                 "fdf! must be a device objective handle (RosenbrockGPU, SparseLSGPU, LogRegGPU, ...): "
@@ -57,8 +58,12 @@ class MinimizerRun:
         self.β_config = config.β_config
         lbfgs_m = self.β_config.m if isinstance(self.β_config, LBFGS) else 0
         # ## allocate + Step 1: x = copy(x_initial); f_x = fdf!(df_x, x); norm(df_x)   :20-26
+        kw = {"quadratic_linesearch": True} if quadratic_linesearch else {}
+        if quadratic_linesearch and isinstance(linesearch_config, geometric.Backtracking):
+            raise TypeError("the quadratic-aware path needs a line search that accepts its last trial "
+                            "(Backtracking adopts a rejected one, geometric.jl:141-144)")
         self.info = fdf_.make_workspace(x_initial, lbfgs_m=lbfgs_m, fuse_direction=fuse_direction,
-                                        beta_form=beta_form)
+                                        beta_form=beta_form, **kw)
         info = self.info
         self.x, self.df_x = info.x, info.df_x
         self.f_x = info.f_x0
@@ -107,6 +112,10 @@ class MinimizerRun:
 
         # numerically valid proposed iterate?                               :107-121
         self.norm_df_xp = info.norm_df_xp()
+        if getattr(info, "quadratic", False):
+            # the trials were evaluated from the parabola ½r·r + a r·v + ½a² v·v, which cancels badly once
+            # f has dropped by many orders of magnitude; the accepted step's own ½ Σ r² is now known
+            f_xp = f64(info.pack[P_PHI])
         if not np.isfinite(f_xp) or not np.isfinite(self.norm_df_xp):
             return self._finish(n - 1, "non_finite_objective_or_gradient_proposed")
 
@@ -136,7 +145,8 @@ class MinimizerRun:
 
 
 def minimizeobjective(fdf_, x_initial, config: CGConfig, linesearch_config: LineSearchConfig, *,
-                      fuse_direction: bool = True, beta_form: str = "fused") -> Results:
+                      fuse_direction: bool = True, beta_form: str = "fused",
+                      quadratic_linesearch: bool = False) -> Results:
     """minimizeobjective (src/engine/optim.jl:6-171).
 
     `fdf_` is a device objective handle; `x_initial` a host vector (this rank's shard); the
@@ -144,9 +154,13 @@ def minimizeobjective(fdf_, x_initial, config: CGConfig, linesearch_config: Line
     reference): `fuse_direction` defers updatedir! into the next trial kernel (bitwise identical
     result, 24n fewer bytes per iteration); `beta_form="literal"` evaluates the HZ / YWS β
     exactly as cg_flavours.jl:71-76 writes it (one extra pass) instead of the algebraically
-    equal pack form.
+    equal pack form; `quadratic_linesearch` (CSR least squares) evaluates the trials
+    of each line search from v = A u — one SpMV and one SpMVᵀ per iteration whatever the number of
+    trials; ϕ then comes from ½r·r + a r·v + ½a² v·v, so decisions agree with the plain path up to
+    rounding.
     """
-    run = MinimizerRun(fdf_, x_initial, config, linesearch_config, fuse_direction, beta_form)
+    run = MinimizerRun(fdf_, x_initial, config, linesearch_config, fuse_direction, beta_form,
+                       quadratic_linesearch)
     run.run()
     ret = run.results()
     run.info.close()

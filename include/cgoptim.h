@@ -193,6 +193,16 @@ int cgo_lbfgs_update_dir(cgo_state *st, double out[CGO_PACK_LEN]);
 int cgo_solvesys_begin(cgo_state *st);
 int cgo_solvesys_project(cgo_state *st, double m, int32_t fix_stale_iterate, double out[CGO_PACK_LEN]);
 int cgo_solvesys_accept(cgo_state *st, int32_t fix_stale_iterate);
+/* Quadratic-aware line search for ½‖Ax − b‖²: along x + a u the residual is r + a·Au,
+ * so after ONE SpMV every trial of linesearch! (nocedal.jl:33-209, wolfe.jl:13-165) is scalar arithmetic:
+ * ϕ(a) = ½ r·r + a r·v + ½ a² v·v, dϕ(a) = r·v + a v·v, v = A u.
+ *   cgo_quad_begin   v = A u;  out[0] = r·v, out[1] = v·v, out[2] = r·r   (r: residual at x)
+ *   cgo_quad_accept  the accepted step: xp = x + a u, r += a v, g⁺ = Aᵀ r and the pack of cgo_eval_trial
+ *                    (CGO_P_PHI = ½ Σ r²), after which cgo_accept adopts (xp, g⁺) as usual.
+ * One SpMV + one SpMVᵀ per iteration whatever the number of trials; decisions agree with the plain
+ * path up to rounding of ϕ (tests/test_gpu_sparse_ls.py). */
+int cgo_quad_begin(cgo_state *st, double out[CGO_PACK_LEN]);
+int cgo_quad_accept(cgo_state *st, double a, double out[CGO_PACK_LEN]);
 /* Hessian-vector product along the current direction, hv = ∇²f(x) u (CSR least squares: Aᵀ(A u), two
  * SpMV launches; the curvature a quadratic-aware line search needs — the reference engine itself
  * never forms one, src/engine/optim.jl:83-145).  out[0] = u·Hu (as ‖Au‖²), out[1] = u·hv, out[2] = hv·hv;

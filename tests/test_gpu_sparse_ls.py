@@ -252,3 +252,49 @@ def test_hessian_vector_product_and_exact_line_minimum(ctx):
     with pytest.raises(cg.CgoError):
         w2.hessvec_dir()
     w2.close(); ro.close(); obj.close()
+
+
+@pytest.mark.parametrize("flavour,linesearch", [("HagerZhang", "StrongWolfeBisection"), ("LBFGS", "Wolfe"),
+                                                 ("LiuStorrey", "YuanWeiLuWolfe")])
+def test_quadratic_aware_linesearch_matches_plain_path(ctx, flavour, linesearch):
+    """with v = A u known, every trial of a line search is scalar arithmetic.  The
+    decisions (step sizes, evaluation counts) must be those of the plain path, the objective within
+    rounding of it, and each iteration must cost exactly one SpMV and one SpMVᵀ however many trials."""
+    n = 40_000
+    obj = cg.SparseLSGPU(n, 10, 1024, 24, 0, ctx)
+    _, cfg, ls = make_pair(flavour, linesearch, max_iters=40, eps=1e-9)
+    x0 = np.zeros(n)
+    plain = cg.minimizeobjective(obj, x0, cfg, ls)
+    ctx.timing(True)
+    ctx.timing_read(reset=True)
+    quad = cg.minimizeobjective(obj, x0, cfg, ls, quadratic_linesearch=True)
+    t = ctx.timing_read(reset=True)
+    ctx.timing(False)
+    k = min(len(plain.trace.objective), len(quad.trace.objective), 30)
+    assert k >= 10
+    assert np.array_equal(quad.trace.step_size[:k], plain.trace.step_size[:k])
+    assert np.array_equal(quad.trace.objective_evals[:k], plain.trace.objective_evals[:k])
+    # r is carried forward as r + a v instead of being recomputed as A xp − b (the recursive residual of
+    # every CG code): it drifts by ≈ ε‖r₀‖ per step, i.e. f = ½‖r‖² by ≈ ε √(f f₀), which only shows once f
+    # has fallen by twenty orders of magnitude
+    fp, fq, f0 = plain.trace.objective[:k], quad.trace.objective[:k], plain.trace.objective[0]
+    assert np.all(np.abs(fq - fp) <= 1e-9 * fp + 1e-14 * np.sqrt(fp * f0))
+    gp_, gq = plain.trace.grad_norm[:k], quad.trace.grad_norm[:k]
+    assert np.all(np.abs(gq - gp_) <= 1e-7 * gp_ + 1e-13 * gp_[0])
+    assert quad.status == plain.status and abs(quad.iters_ran - plain.iters_ran) <= 2
+    iters, evals = quad.iters_ran, int(quad.trace.objective_evals.sum())
+    assert evals > iters                                   # some line searches needed several trials …
+    assert t["spmv"][1] <= iters + 2 and t["spmvT"][1] <= iters + 2      # … but each cost one SpMV + one SpMVᵀ
+    obj.close()
+
+
+def test_quadratic_aware_linesearch_rejects_what_it_cannot_do(ctx):
+    obj = cg.SparseLSGPU(2000, 10, 64, 24, 0, ctx)
+    _, cfg, ls = make_pair("HagerZhang", "Backtracking")
+    with pytest.raises(TypeError):
+        cg.minimizeobjective(obj, np.zeros(2000), cfg, ls, quadratic_linesearch=True)
+    ro = cg.RosenbrockGPU(64, ctx)
+    _, cfg, ls = make_pair("HagerZhang")
+    with pytest.raises(cg.CgoError):
+        cg.minimizeobjective(ro, np.zeros(64), cfg, ls, quadratic_linesearch=True)
+    obj.close(); ro.close()
