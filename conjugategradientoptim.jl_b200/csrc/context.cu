@@ -74,6 +74,7 @@ extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
     cudaDeviceProp prop;
     CGO_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sms = prop.multiProcessorCount;
+    if (const char *e = getenv("CGO_CSR_PASS_OCC")) c->csr_pass_occ = (e[0] == '3') ? 3 : 2;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {

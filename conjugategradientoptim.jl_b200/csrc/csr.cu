@@ -92,13 +92,16 @@ constexpr int TS_THREADS = CGO_B + 32;
 constexpr int TS_OCC = 2;
 constexpr int TS_UN = 10;                   // gathers in flight per lane
 constexpr int TS_SMEM_BUDGET = 115200;      // two CTAs per SM (228 KB - 2 x 1 KB reserved)
-template <int NOPS>
+// OCC CTAs per SM: 2 for the streaming-bound kernels (a ring of ~3 tiles of 10 entries per row);
+// 3 for the short rows of a column-block pass, which are gather-latency bound and want more warps
+template <int NOPS, int OCC = TS_OCC>
 struct TsLayout {
+    static constexpr int BUDGET = OCC == 2 ? TS_SMEM_BUDGET : (228 * 1024) / OCC - 1024 - 256;
     static constexpr int RP_BYTES = (CGO_B + 2) * 8;
     static constexpr int OP_BYTES = CGO_B * 8;
     static constexpr int DESC_BYTES = RP_BYTES + NOPS * OP_BYTES;
     static constexpr int TAIL_BYTES = 2 * TS_ND * 8 + TS_ND * 4 + CGO_MAXK * CGO_NW * 8;
-    static constexpr int RING = ((TS_SMEM_BUDGET - TS_ND * DESC_BYTES - TAIL_BYTES - 64) / 12) & ~3;
+    static constexpr int RING = ((BUDGET - TS_ND * DESC_BYTES - TAIL_BYTES - 64) / 12) & ~3;
     static constexpr int CHMAX = (RING / 2) & ~3;
     // byte offsets (all multiples of 16)
     static constexpr int OFF_VAL = 0;
@@ -108,7 +111,7 @@ struct TsLayout {
     static constexpr int OFF_LEN = OFF_BAR + 2 * TS_ND * 8;
     static constexpr int OFF_RED = (OFF_LEN + TS_ND * 4 + 15) & ~15;
     static constexpr int BYTES = OFF_RED + CGO_MAXK * CGO_NW * 8;
-    static_assert(BYTES <= TS_SMEM_BUDGET && RP_BYTES % 16 == 0 && DESC_BYTES % 16 == 0, "smem layout");
+    static_assert(BYTES <= BUDGET && RP_BYTES % 16 == 0 && DESC_BYTES % 16 == 0, "smem layout");
 };
 
 __device__ __forceinline__ bool ts_next_tile(int &v, int64_t &tile, int nact, int64_t ntiles, int G) {
@@ -144,12 +147,12 @@ __device__ __forceinline__ double ld_gather_f64_if(const double *p, uint64_t pol
     return r;
 }
 
-template <class Epi>
-__global__ void __launch_bounds__(TS_THREADS, TS_OCC)
+template <class Epi, int OCC>
+__global__ void __launch_bounds__(TS_THREADS, OCC)
 k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
     constexpr int K = Epi::K;
     constexpr int NOPS = Epi::NOPS;
-    using L = TsLayout<NOPS>;
+    using L = TsLayout<NOPS, OCC>;
     constexpr int RING = L::RING, CHMAX = L::CHMAX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_val = reinterpret_cast<double *>(smem_raw + L::OFF_VAL);
@@ -300,21 +303,31 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
     cgo_grid_finish<K, BarLanes>(red, nact, s_red, bar);
 }
 
-template <class Epi>
-static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
+template <class Epi, int OCC>
+static int launch_csr_occ(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
     const int64_t ntiles = (A.nrows + CGO_B - 1) / CGO_B;
     int64_t nact = ntiles < red.G ? ntiles : red.G;
-    int64_t phys = (int64_t)c->sms * TS_OCC;
+    int64_t phys = (int64_t)c->sms * OCC;
     int grid = (int)(nact < phys ? nact : phys);
     if (grid < 1) grid = 1;
-    const size_t smem = TsLayout<Epi::NOPS>::BYTES;
-    CGO_CUDA(cudaFuncSetAttribute(k_csr_rows<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = TsLayout<Epi::NOPS, OCC>::BYTES;
+    CGO_CUDA(cudaFuncSetAttribute(k_csr_rows<Epi, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cgo_timer_begin(c, tclass);
-    k_csr_rows<Epi><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red);
+    k_csr_rows<Epi, OCC><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red);
     cgo_timer_end(c);
     c->launches++;
     CGO_CUDA(cudaGetLastError());
     return 0;
+}
+template <class Epi>
+static int launch_csr(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
+    return launch_csr_occ<Epi, TS_OCC>(c, A, xg, epi, red, tclass);
+}
+// a column-block pass: short rows, gather-latency bound
+template <class Epi>
+static int launch_csr_pass(cgo_ctx *c, const CsrMat &A, const double *xg, const Epi &epi, const RedArgs &red, int tclass) {
+    if (c->csr_pass_occ == 3) return launch_csr_occ<Epi, 3>(c, A, xg, epi, red, tclass);
+    return launch_csr_occ<Epi, TS_OCC>(c, A, xg, epi, red, tclass);
 }
 
 // ------------------------------------------------------------------ row epilogues
@@ -887,16 +900,17 @@ static int launch_csr_blocked(cgo_ctx *c, const CsrMat &A, const CsrBlocked &B, 
     if (B.blk.empty()) return launch_csr(c, A, xg, epi, red, tclass);
     const size_t nb = B.blk.size();
     RedArgs scratch = cgo_red_args(c, CGO_PACK_LEN - 1);
+    if (c->csr_pass_occ == 3) scratch.G = c->sms * 3;     // nothing is reduced in these passes: any sweep order will do
     if (wait_first) {
         scratch.wait0 = red.wait0; scratch.wait1 = red.wait1; scratch.wait_all = red.wait_all;
         scratch.wait_val = red.wait_val; scratch.nranks = red.nranks;
     }
     for (size_t j = 0; j + 1 < nb; ++j) {
         EpiStore es{partial};
-        if (j == 0) CGO_TRY(launch_csr(c, B.blk[j], xg, es, scratch, tclass));
-        else CGO_TRY(launch_csr(c, B.blk[j], xg, with_init(es, partial), scratch, tclass));
+        if (j == 0) CGO_TRY(launch_csr_pass(c, B.blk[j], xg, es, scratch, tclass));
+        else CGO_TRY(launch_csr_pass(c, B.blk[j], xg, with_init(es, partial), scratch, tclass));
     }
-    return launch_csr(c, B.blk[nb - 1], xg, with_init(epi, partial), red, tclass);
+    return launch_csr_pass(c, B.blk[nb - 1], xg, with_init(epi, partial), red, tclass);
 }
 
 // ------------------------------------------------------------------ the objective

@@ -72,6 +72,7 @@ struct cgo_ctx {
     bool own_stream = false;
     int G = 296;
     size_t gather_block_bytes = (size_t)40 << 20;   // column-block size of large random gathers (csr.cu)
+    int csr_pass_occ = 2;                           // CTAs per SM of the column-block passes (CGO_CSR_PASS_OCC=3 to try 3)
     int64_t launches = 0;
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax
