@@ -700,10 +700,11 @@ extern "C" int cgo_obj_barrier_infeasible(cgo_obj *obj, const double *x_host, in
 }
 
 // ------------------------------------------------------------------ solver state
+static size_t vec_bytes(const cgo_state *st) { return sizeof(double) * (size_t)(st->n + 2 * st->halo + 4); }
 static int alloc_vec(cgo_state *st, double **base, double **ptr) {
-    size_t len = (size_t)(st->n + 2 * st->halo + 4);
-    CGO_CUDA(cudaMalloc(base, sizeof(double) * len));
-    CGO_CUDA(cudaMemsetAsync(*base, 0, sizeof(double) * len, st->ctx->stream));
+    void *p = nullptr;
+    CGO_TRY(cgo_dev_alloc(st->ctx, vec_bytes(st), &p));
+    *base = (double *)p;
     *ptr = *base + st->halo;
     return 0;
 }
@@ -720,10 +721,11 @@ extern "C" int cgo_state_destroy(cgo_state *st) {
             cgo_peer_free(st->ctx, mine, st->xpeers[k], true);
         }
     }
-    for (int i = 0; i < 5; ++i) cudaFree(st->base[i]);
-    for (auto p : st->S) cudaFree(p);
-    for (auto p : st->Y) cudaFree(p);
-    cudaFree(st->q);
+    for (int i = 0; i < 5; ++i) cgo_dev_free(st->ctx, st->base[i], vec_bytes(st));
+    const size_t hist_bytes = sizeof(double) * (size_t)(st->n + 4);
+    for (auto p : st->S) cgo_dev_free(st->ctx, p, hist_bytes);
+    for (auto p : st->Y) cgo_dev_free(st->ctx, p, hist_bytes);
+    cgo_dev_free(st->ctx, st->q, hist_bytes);
     cudaFree(st->xn);
     cudaFree(st->hv);
     delete st;
@@ -759,19 +761,18 @@ extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, in
     st->xp_alloc = 1;
     st->m = lbfgs_m;
     if (lbfgs_m > 0) {
-        size_t len = (size_t)(st->n + 4);
+        const size_t hist_bytes = sizeof(double) * (size_t)(st->n + 4);
         for (int k = 0; k < lbfgs_m; ++k) {
-            double *s = nullptr, *y = nullptr;
-            CGO_CUDA(cudaMalloc(&s, sizeof(double) * len));
-            st->S.push_back(s);
-            CGO_CUDA(cudaMalloc(&y, sizeof(double) * len));
-            st->Y.push_back(y);
-            CGO_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * len, ctx->stream));
-            CGO_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * len, ctx->stream));
+            void *s = nullptr, *y = nullptr;
+            CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &s));
+            st->S.push_back((double *)s);
+            CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &y));
+            st->Y.push_back((double *)y);
         }
         st->rho.assign(lbfgs_m, 0.0);
-        CGO_CUDA(cudaMalloc(&st->q, sizeof(double) * len));
-        CGO_CUDA(cudaMemsetAsync(st->q, 0, sizeof(double) * len, ctx->stream));
+        void *q = nullptr;
+        CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &q));
+        st->q = (double *)q;
     }
     // optim.jl:21 x = copy(x_initial); :25 f_x = fdf!(df_x, x): evaluate at x0 through the trial
     // kernels with u = 0, a = 0 (xp = x0 + 0*0 = x0 exactly), then adopt (xp, g⁺) as (x, g).

@@ -105,6 +105,7 @@ extern "C" int cgo_ctx_destroy(cgo_ctx *c) {
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)c->comm);
     cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFreeHost(c->h_pack);
     cudaFree(c->d_pack); cudaFree(c->d_gather); cudaFree(c->d_scal);
+    for (auto &kv : c->dev_pool) for (void *p : kv.second) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto &t : c->pending) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -195,6 +196,29 @@ extern "C" int cgo_ctx_peer_memory(cgo_ctx *c, int *enabled) {
     CGO_CHECK(c && enabled, "NULL argument");
     *enabled = (c->nranks > 1 && c->peer_ok) ? 1 : 0;
     return 0;
+}
+
+// ------------------------------------------------------------------ pooled device blocks
+int cgo_dev_alloc(cgo_ctx *c, size_t bytes, void **out) {
+    auto it = c->dev_pool.find(bytes);
+    if (it != c->dev_pool.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        c->dev_pool_bytes -= bytes;
+    } else {
+        CGO_CUDA(cudaMalloc(out, bytes));
+    }
+    CGO_CUDA(cudaMemsetAsync(*out, 0, bytes, c->stream));
+    return 0;
+}
+void cgo_dev_free(cgo_ctx *c, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (c->dev_pool_bytes + bytes <= ((size_t)24 << 30)) {      // keep at most 24 GB around
+        c->dev_pool[bytes].push_back(ptr);
+        c->dev_pool_bytes += bytes;
+    } else {
+        cudaFree(ptr);
+    }
 }
 
 // ------------------------------------------------------------------ peer memory (CUDA IPC)

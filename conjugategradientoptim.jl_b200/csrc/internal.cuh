@@ -106,7 +106,13 @@ struct cgo_ctx {
     std::map<size_t, std::vector<std::vector<void *>>> peer_pool;   // released blocks by size
     std::map<void *, size_t> peer_bytes;                            // size of every live block
     size_t peer_pool_bytes = 0;
+    // plain device blocks of destroyed states, by size: the next state of the same problem reuses them
+    // (cudaMalloc / cudaFree of 1.6 GB vectors cost milliseconds each and cudaFree synchronises the device)
+    std::map<size_t, std::vector<void *>> dev_pool;
+    size_t dev_pool_bytes = 0;
 };
+int cgo_dev_alloc(cgo_ctx *ctx, size_t bytes, void **out);     // zero-filled (stream-ordered)
+void cgo_dev_free(cgo_ctx *ctx, void *ptr, size_t bytes);
 // flag slots of a rank's block
 // (CGO_F_PACK + r: rank r's scalar pack of the current exchange has landed in my gather block)
 constexpr int CGO_MAX_RANKS = 64;
