@@ -624,7 +624,7 @@ struct BarrierObj : cgo_obj {
     double *lo = nullptr, *hi = nullptr;
     double t = 1.0;
     ~BarrierObj() override {
-        if (ctx) cudaSetDevice(ctx->device);
+        if (ctx && cgo_ctx_alive(ctx)) cudaSetDevice(ctx->device);
         cudaFree(lo); cudaFree(hi);
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
@@ -711,8 +711,12 @@ static int alloc_vec(cgo_state *st, double **base, double **ptr) {
 
 extern "C" int cgo_state_destroy(cgo_state *st) {
     if (!st) return 0;
-    cudaSetDevice(st->ctx->device);
-    cudaStreamSynchronize(st->ctx->stream);
+    if (cgo_ctx_alive(st->ctx)) {
+        cudaSetDevice(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->stream);
+    } else {
+        cudaDeviceSynchronize();
+    }
     if (st->peer_x) {               // collective: the neighbours unmap before the owner frees
         for (int k = 0; k < 2; ++k) {
             if (st->xpeers[k].size() != (size_t)st->ctx->nranks) continue;

@@ -19,6 +19,17 @@ void cgo_set_error(const char *fmt, ...) {
 extern "C" const char *cgo_last_error(void) { return g_err; }
 extern "C" int cgo_version(void) { return 100; }
 
+// ------------------------------------------------------------------ live contexts
+// Host languages with garbage collection may finalise a state or an objective AFTER its ctx
+// (interpreter shutdown, test fixtures): handles check before they touch the ctx.
+#include <mutex>
+#include <set>
+static std::mutex g_live_mu;
+static std::set<cgo_ctx *> g_live;
+static void live_add(cgo_ctx *c) { std::lock_guard<std::mutex> l(g_live_mu); g_live.insert(c); }
+static void live_remove(cgo_ctx *c) { std::lock_guard<std::mutex> l(g_live_mu); g_live.erase(c); }
+bool cgo_ctx_alive(cgo_ctx *c) { std::lock_guard<std::mutex> l(g_live_mu); return g_live.count(c) != 0; }
+
 // ------------------------------------------------------------------ NCCL via dlopen
 struct NcclApi {
     void *handle = nullptr;
@@ -91,12 +102,14 @@ extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
     CGO_CUDA(cudaMemsetAsync(c->d_pack, 0, sizeof(double) * CGO_PACK_LEN, c->stream));
     CGO_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double) * CGO_NSCAL, c->stream));
     CGO_CUDA(cudaStreamSynchronize(c->stream));
+    live_add(c);
     *out = c;
     return 0;
 }
 
 extern "C" int cgo_ctx_destroy(cgo_ctx *c) {
-    if (!c) return 0;
+    if (!c || !cgo_ctx_alive(c)) return 0;
+    live_remove(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->gather_local) cgo_peer_free(c, c->gather_local, c->gather_peer, false);
@@ -213,6 +226,7 @@ int cgo_dev_alloc(cgo_ctx *c, size_t bytes, void **out) {
 }
 void cgo_dev_free(cgo_ctx *c, void *ptr, size_t bytes) {
     if (!ptr) return;
+    if (!cgo_ctx_alive(c)) { cudaFree(ptr); return; }
     if (c->dev_pool_bytes + bytes <= ((size_t)24 << 30)) {      // keep at most 24 GB around
         c->dev_pool[bytes].push_back(ptr);
         c->dev_pool_bytes += bytes;
@@ -273,6 +287,7 @@ int cgo_peer_alloc(cgo_ctx *c, size_t bytes, void **local, std::vector<void *> &
 }
 int cgo_peer_free(cgo_ctx *c, void *local, std::vector<void *> &peers, bool collective) {
     if (!local) return 0;
+    if (!cgo_ctx_alive(c)) { peers.clear(); return 0; }      // the ctx went first: the block dies with the process
     if (c->nranks > 1 && collective && peers.size() == (size_t)c->nranks) {
         // keep the block and its mappings for the next allocation of this size; the barrier makes
         // sure no rank still reads or writes it on behalf of the old owner

@@ -942,7 +942,7 @@ struct CsrObj : cgo_obj {
     void **d_grecv_dst = nullptr;      // rank r's g_recv + me * part_stride
     int64_t *d_flo = nullptr;
     ~CsrObj() override {
-        if (ctx) cudaSetDevice(ctx->device);
+        if (ctx && cgo_ctx_alive(ctx)) cudaSetDevice(ctx->device);
         csr_free(A); csr_free(AT);
         Ab.free_all(); ATb.free_all();
         if (r_is_peer) { cgo_peer_free(ctx, r_base, rpeers, true); r_base = nullptr; }

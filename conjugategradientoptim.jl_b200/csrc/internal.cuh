@@ -111,6 +111,7 @@ struct cgo_ctx {
     std::map<size_t, std::vector<void *>> dev_pool;
     size_t dev_pool_bytes = 0;
 };
+bool cgo_ctx_alive(cgo_ctx *ctx);                               // false once cgo_ctx_destroy ran (GC-ordered finalisers)
 int cgo_dev_alloc(cgo_ctx *ctx, size_t bytes, void **out);     // zero-filled (stream-ordered)
 void cgo_dev_free(cgo_ctx *ctx, void *ptr, size_t bytes);
 // flag slots of a rank's block
