@@ -491,7 +491,7 @@ __global__ void k_pack_exchange(const double *pack, void *const *gather_peer, vo
     __syncthreads();
     if (t < nranks) {
         cgo_st_release_sys((unsigned long long *)flags_peer[t] + CGO_F_PACK + me, epoch);
-        while (cgo_ld_acquire_sys(flags_local + CGO_F_PACK + t) < epoch) __nanosleep(32);
+        cgo_spin_until(flags_local + CGO_F_PACK + t, epoch);
     }
     __syncthreads();
     if (t < K) {

@@ -95,17 +95,25 @@ __device__ __forceinline__ void cgo_grid_finish(const RedArgs &red, int nact, do
     }
 }
 
+// spin until *flag >= val.  Ranks run in lockstep, so a wait lasts micro- to milliseconds; a peer that
+// died (host exception, killed process) must not leave this GPU spinning for ever: after ≈30 s the
+// kernel traps and the next CUDA call of this rank reports the failure.
+__device__ __forceinline__ void cgo_spin_until(const unsigned long long *flag, unsigned long long val) {
+    unsigned int polls = 0;
+    while (cgo_ld_acquire_sys(flag) < val) {
+        __nanosleep(128);
+        if (++polls > (1u << 28)) asm volatile("trap;");
+    }
+}
 // consumer side of the hand-off: thread 0 spins on the local flags, `bar` releases the others
 template <class Bar>
 __device__ __forceinline__ void cgo_wait_flags(const RedArgs &red, Bar bar) {
     if (red.wait0 == nullptr && red.wait_all == nullptr) return;
     if (threadIdx.x == 0 && red.wait0 != nullptr) {
-        while (cgo_ld_acquire_sys(red.wait0) < red.wait_val) __nanosleep(64);
-        if (red.wait1 != nullptr)
-            while (cgo_ld_acquire_sys(red.wait1) < red.wait_val) __nanosleep(64);
+        cgo_spin_until(red.wait0, red.wait_val);
+        if (red.wait1 != nullptr) cgo_spin_until(red.wait1, red.wait_val);
     }
-    if (red.wait_all != nullptr && (int)threadIdx.x < red.nranks)
-        while (cgo_ld_acquire_sys(red.wait_all + threadIdx.x) < red.wait_val) __nanosleep(64);
+    if (red.wait_all != nullptr && (int)threadIdx.x < red.nranks) cgo_spin_until(red.wait_all + threadIdx.x, red.wait_val);
     bar();
 }
 
