@@ -88,6 +88,23 @@ def _worker(rank, world, port, q):
         if not same:
             ok = False
             msgs.append(f"{flavour}/{linesearch} rank {rank}: {ret.status}/{ora.status} {ret.iters_ran}/{ora.iters_ran}")
+    # the callers next to the hot path, sharded the same way: solvesystem (as written and as published)
+    for fix in (False, True):
+        lo, hi = cg.shard_range(n, world, rank, 2)
+        ocfg, cfg, _ = make_pair("YuanWangSheng", max_iters=6)
+        x0 = O.rosenbrock_x0(n, 24, 0.1)
+        O.set_cgo_order(296, 1)
+        ret = cg.solvesystem(ShardedObjective(LocalRosenbrock(hi - lo)), x0[lo:hi], cfg,
+                             cg.setupLinesearchSolveSys(1.0), fix_stale_iterate=fix)
+        O.set_cgo_order(296, world)
+        ora = O.solvesystem(O.Objective.rosenbrock(n), x0, ocfg, O.solvesys_ls(1.0, fix_stale_iterate=fix))
+        same = (ret.status == ora.status and ret.iters_ran == ora.iters_ran
+                and np.array_equal(ret.trace.objective, ora.trace_objective)
+                and np.array_equal(ret.trace.objective_evals, ora.trace_objective_evals)
+                and np.array_equal(ret.minimizer, ora.minimizer[lo:hi]))
+        if not same:
+            ok = False
+            msgs.append(f"solvesystem fix={fix} rank {rank}: {ret.status}/{ora.status} {ret.iters_ran}/{ora.iters_ran}")
     # shard ranges tile [0, n) with even boundaries
     bounds = [cg.shard_range(1_000_006, world, r, 2) for r in range(world)]
     ok = ok and bounds[0][0] == 0 and bounds[-1][1] == 1_000_006
