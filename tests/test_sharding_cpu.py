@@ -89,9 +89,10 @@ def _worker(rank, world, port, q):
             ok = False
             msgs.append(f"{flavour}/{linesearch} rank {rank}: {ret.status}/{ora.status} {ret.iters_ran}/{ora.iters_ran}")
     # the callers next to the hot path, sharded the same way: solvesystem (as written and as published)
+    n = 3000
     for fix in (False, True):
         lo, hi = cg.shard_range(n, world, rank, 2)
-        ocfg, cfg, _ = make_pair("YuanWangSheng", max_iters=6)
+        ocfg, cfg, _ = make_pair("YuanWangSheng", max_iters=4)
         x0 = O.rosenbrock_x0(n, 24, 0.1)
         O.set_cgo_order(296, 1)
         ret = cg.solvesystem(ShardedObjective(LocalRosenbrock(hi - lo)), x0[lo:hi], cfg,
