@@ -16,17 +16,25 @@ solvesys_accept!(ws::DeviceWorkspace; fix_stale_iterate::Bool = false) =
 
 # linesearch! (solve_system.jl:29-55) on the device container: same loop, evalϕdϕ! is one launch
 function CGO.linesearch!(info::DeviceWorkspace, config::CGO.LinesearchSolveSys{Float64}, fdf!::DeviceObjective)
-    hint_first_trial!(info, config.s)
+    info.hint = config.s                                                  # the first trial is always a = s·ρ⁰
     norm_u_sq = dot_u_u(info)                                             # :39
     for i = 0:config.max_iters-1                                          # :41
         a = config.s * config.ρ^i                                         # :42
         f_xp, dϕ_xp = evaltrial!(info, a)                                 # :44
         norm_df_xp = sqrt(info.pack[P_GPGP])                              # :47
         if !(-dϕ_xp < config.σ * a * norm_df_xp * norm_u_sq)              # :48
-            return f_xp, norm_df_xp, a, i, true
+            return f_xp, norm_df_xp, a, i, true                           # :50
         end
     end
     return NaN, NaN, NaN, config.max_iters - 1, false                     # (:54 is an UndefVarError in the reference)
+end
+
+"info.xp, info.df_xp on the host (updateresult! with the container, types.jl:116-131)"
+function download_trial(ws::DeviceWorkspace)
+    x, g = Vector{Float64}(undef, ws.n), Vector{Float64}(undef, ws.n)
+    check(ccall((:cgo_download_vector, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), ws.h, 3, x))
+    check(ccall((:cgo_download_vector, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), ws.h, 4, g))
+    return x, g
 end
 
 """
@@ -34,32 +42,47 @@ solvesystem (src/engine/solve_system.jl:64-239) for a device objective: the refe
 its vector lines replaced by the three calls above; `fix_stale_iterate = true` projects from the
 current iterate (Alg. 3.1 as published) instead of from `x_next` (:171-177 as written).
 """
-function CGO.solvesystem(fdf!::DeviceObjective, x_initial::Vector{Float64}, config::CGO.CGConfig,
-                         linesearch_config::CGO.LinesearchSolveSys{Float64}; fix_stale_iterate::Bool = false)
-    info = DeviceWorkspace(fdf!, x_initial)
-    solvesys_begin!(info)
+function CGO.solvesystem(fdf!::DeviceObjective, x_initial::Vector{Float64}, config::CGConfig{Float64,BT,ET},
+                         linesearch_config::CGO.LinesearchSolveSys{Float64};
+                         fix_stale_iterate::Bool = false) where {BT<:CGβConfig,ET}
+    max_iters, β_config = config.max_iters, config.β_config               # :74-75
+    info = DeviceWorkspace(fdf!, x_initial)                               # :80-87
+    solvesys_begin!(info)                                                 # :82
+    x, df_x = vec(info, :x), vec(info, :df_x)
     f_x, norm_df_x = info.f_x0, info.norm_df_x0
-    ret = devresults(info, f_x, config)                                   # :93-101
-    resetdirection!(info)                                                 # :104-105
-    for n = 1:config.max_iters                                            # :109
-        norm_df_x < config.ϵ && return finish!(ret, info, f_x, n - 1, :success)                      # :112-123
-        f_xp, norm_df_xp, a_star, evals, ok = CGO.linesearch!(info, linesearch_config, fdf!)         # :126-130
-        ok || return finish!(ret, info, f_x, n - 1, :linesearch_failed)                              # :131-142
-        if norm_df_xp < config.ϵ                                                                      # :146-168
-            CGO.updatetrace!(ret.trace, f_xp, norm_df_xp, a_star, evals, n)
-            return finish!(ret, info, f_xp, n, :success; from_trial = true)
-        end
-        m = a_star * info.pack[P_DPHI] / norm_df_xp^2                                                 # :246
-        f_x_next, norm_next = solvesys_project!(info, m; fix_stale_iterate)                           # :171-179
-        (isfinite(f_x_next) && isfinite(norm_next)) ||
-            return finish!(ret, info, f_x, n - 1, :non_finite_objective_or_gradient_proposed)        # :180-194
-        β = CGO.getβ(config.β_config, DeviceVector(info, :df_xp), DeviceVector(info, :df_x), DeviceVector(info, :u))   # :201-206
-        solvesys_accept!(info; fix_stale_iterate)                                                     # :196, :207-208
-        f_x, norm_df_x = f_x_next, norm_next                                                          # :197, :209
-        CGO.updatedir!(DeviceVector(info, :u), DeviceVector(info, :df_x), β)                          # :212
-        CGO.updatetrace!(ret.trace, f_x, norm_df_x, a_star, evals, n)                                 # :215-222
+    ret = Results(f_x, Float64[], Float64[], 0, :incomplete, setuptrace(Float64, config.trace_status))   # :93-101
+    resizetrace!(ret.trace, max_iters)
+    initializeLineSearchContainer!(info, β_config, df_x, x)               # :104-105
+
+    finish!(f, i, status; from_trial = false) = begin                     # updateresult!, types.jl:116-151
+        ret.objective = f
+        ret.minimizer, ret.gradient = from_trial ? download_trial(info) : download(info)
+        ret.iters_ran, ret.status = i, status
+        from_trial || resizetrace!(ret.trace, i)
+        close!(info)
+        ret
     end
-    return finish!(ret, info, f_x, config.max_iters, :max_iters_reached)                              # :225-233
+
+    for n = 1:max_iters                                                   # :109
+        norm_df_x < config.ϵ && return finish!(f_x, n - 1, :success)      # :112-123
+        f_xp, norm_df_xp, a_star, evals, ok = linesearch!(info, linesearch_config, fdf!)             # :126-130
+        ok || return finish!(f_x, n - 1, :linesearch_failed)              # :131-142
+        if norm_df_xp < config.ϵ                                          # :146-168
+            resizetrace!(ret.trace, n)
+            updatetrace!(ret.trace, f_xp, norm_df_xp, a_star, evals, n)
+            return finish!(f_xp, n, :success; from_trial = true)
+        end
+        m = a_star * info.pack[P_DPHI] / norm_df_xp^2                     # :246
+        f_x_next, norm_next = solvesys_project!(info, m; fix_stale_iterate = fix_stale_iterate)      # :171-179
+        (isfinite(f_x_next) && isfinite(norm_next)) ||
+            return finish!(f_x, n - 1, :non_finite_objective_or_gradient_proposed)                   # :180-194
+        β = getβ(β_config, vec(info, :df_xp), df_x, vec(info, :u))        # :201-206
+        solvesys_accept!(info; fix_stale_iterate = fix_stale_iterate)     # :196, :207-208
+        f_x, norm_df_x = f_x_next, norm_next                              # :197, :209
+        updatedir!(vec(info, :u), df_x, β)                                # :212
+        updatetrace!(ret.trace, f_x, norm_df_x, a_star, evals, n)         # :215-222
+    end
+    return finish!(f_x, max_iters, :max_iters_reached)                    # :225-233
 end
 
 # ---------------------------------------------------------------- primal barrier (src/engine/primal_barrier.jl)
