@@ -234,6 +234,28 @@ def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
     return evals * per_eval + 16.0 * n_local * iters
 
 
+def ncu_traffic(args, world, n):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very
+    configuration (profiles/, taken with the command in scratch/profile_r1.sh); None for any other configuration."""
+    name = {"sparse_ls": ("r1_ncu_full_ls_r1b.txt", 200_000_000), "rosenbrock": ("r1_ncu_full_rosen_r1.txt", 100_000_000)}
+    if world != 1 or args.workload not in name or n != name[args.workload][1] or (args.workload == "sparse_ls" and args.coh < 28):
+        return None, None
+    path = os.path.join(ROOT, "profiles", name[args.workload][0])
+    try:
+        rd, wr = [], []
+        for line in open(path):
+            t = line.split()
+            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+                (rd if t[0].endswith("read.sum") else wr).append(v)
+        if not rd or len(rd) != len(wr):
+            return None, None
+        return round(sum(r + w for r, w in zip(rd, wr)) / len(rd), 1), \
+            f"bytes per launch, mean of {len(rd)} launches: dram__bytes_read.sum + dram__bytes_write.sum, profiles/{name[args.workload][0]}"
+    except OSError:
+        return None, None
+
+
 def logreg_bytes(args, d_loc, nnz_loc):
     """(algorithmic bytes of one fdf! on this rank, of which the K_b + K_c launch pair)
     one rank:  K_a 24d | K_b A + gather w 8d + R y 8N + W c 8N | K_c Aᵀ + gather c 8N + R u,g,w 24d + W g⁺ 8d
@@ -371,9 +393,11 @@ def run_ours(args):
         # per launch pair: 2 x matrix stream + (gather 8n + R b 8n + W r 8n) + (gather 8n + R u,g 16n + W g+ 8n)
         dom_bytes = (dom_cnt / 2.0) * (2 * matrix_bytes(n_local, nnz_local) + 56.0 * n_local)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(args, world, n)
     total_bytes = algorithmic_bytes(args, n_local, nnz_local, evals, K)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": round(dom_bytes / max(dom_cnt, 1), 1), "peak_source": peak_src,
                 "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
