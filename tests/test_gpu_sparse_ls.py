@@ -224,6 +224,30 @@ def test_large_n_properties(ctx, n):
     obj.close()
 
 
+def test_full_size_properties_n2e8(ctx):
+    """BASELINE.json configs[2] at its full size (n = 2e8, 2e9 nonzeros, 60 GB of matrices), through
+    properties that need no oracle run: r(x_true) = 0 exactly (b was built by the same row sums) ⇒
+    f = 0 and g = 0 bit for bit; f(0) > 0; CG decreases f monotonically; two runs are bit-identical."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    n = 200_000_000
+    obj = cg.SparseLSGPU(n, 10, None, 24, 30, ctx)
+    xt = O.sparse_ls_xtrue(n, 24)
+    ws = obj.make_workspace(xt, fuse_direction=False)
+    assert ws.f_x0 == 0.0 and ws.norm_df_x0 == 0.0
+    ws.close()
+    del xt
+    _, cfg, ls = make_pair(max_iters=4)
+    x0 = np.zeros(n)
+    r1 = cg.minimizeobjective(obj, x0, cfg, ls)
+    r2 = cg.minimizeobjective(obj, x0, cfg, ls)
+    assert r1.trace.objective[0] > 0 and np.all(np.diff(r1.trace.objective) < 0)
+    assert np.array_equal(r1.trace.objective, r2.trace.objective) and np.array_equal(r1.trace.step_size, r2.trace.step_size)
+    assert np.array_equal(r1.minimizer, r2.minimizer)
+    obj.close()
+
+
 def test_hessian_vector_product_and_exact_line_minimum(ctx):
     """north_star's Hessian-vector product of the least-squares objective: hv = Aᵀ(A u) through the
     production SpMV kernels, against scipy; and what it is for — on a quadratic,
