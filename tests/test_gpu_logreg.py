@@ -122,3 +122,27 @@ def test_column_blocked_passes_are_bit_identical(block_elems):
     assert ra.status == rb.status and np.array_equal(ra.trace.objective, rb.trace.objective)
     assert np.array_equal(ra.trace.step_size, rb.trace.step_size) and np.array_equal(ra.minimizer, rb.minimizer)
     a.close(); b.close(); c0.close(); c1.close()
+
+
+def test_full_size_properties_cfg4():
+    """BASELINE.json configs[3] at its full size (5e7 samples × 2e7 features, 1e9 nonzeros, column-blocked
+    storage), through properties that need no oracle run: f(0) = log 2 (every sample contributes
+    log1p(e⁰)); the column-blocked passes are in use; L-BFGS decreases f monotonically; two runs are
+    bit-identical."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    c = cg.Context(0)
+    N, d = 50_000_000, 20_000_000
+    obj = cg.LogRegGPU(N, d, 20, 24, 1e-6, c)
+    assert obj.csr_blocks(False) == 4 and obj.csr_blocks(True) == 10
+    _, cfg, ls = make_pair("LBFGS", max_iters=3, c1=1e-4, c2=0.9, lbfgs_m=10)
+    w0 = np.zeros(d)
+    r1 = cg.minimizeobjective(obj, w0, cfg, ls)
+    r2 = cg.minimizeobjective(obj, w0, cfg, ls)
+    ws = obj.make_workspace(w0, fuse_direction=False)
+    assert abs(ws.f_x0 - np.log(2.0)) <= 1e-12
+    ws.close()
+    assert r1.trace.objective[0] < np.log(2.0) and np.all(np.diff(r1.trace.objective) < 0)
+    assert np.array_equal(r1.trace.objective, r2.trace.objective) and np.array_equal(r1.minimizer, r2.minimizer)
+    obj.close(); c.close()
