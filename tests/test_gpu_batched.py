@@ -117,10 +117,12 @@ def test_close_to_single_problem_device_path(ctx):
         assert abs(one.objective - res.objective[p]) <= 1e-10 * abs(one.objective)
 
 
-def test_large_batch_properties(ctx):
-    """32,768 problems (one GPU's share of cfg 5): identical starts give identical results
-    whichever CTA runs them, every problem converges to ones(n), and the run is reproducible."""
-    n, nprob = 512, 32_768
+@pytest.mark.parametrize("nprob", [32_768, 262_144])
+def test_large_batch_properties(ctx, nprob):
+    """32,768 problems (one GPU's share of cfg 5 at 8 GPUs) and the full 262,144 of BASELINE.json
+    configs[4]: identical starts give identical results whichever CTA runs them, every problem
+    converges to ones(n), and the run is reproducible."""
+    n = 512
     X0 = np.tile(_starts(4, n, seed=5), (nprob // 4, 1))
     _, cfg, ls = make_pair("HagerZhang", max_iters=1000)
     a = cg.minimizeobjective_batched(X0, cfg, ls, ctx)
