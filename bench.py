@@ -2,14 +2,16 @@
 """bench.py — CG iterations/s on the BASELINE.json workloads, with roofline and CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload sparse_ls|rosenbrock] [--n N] [--coh C]
+                    [--workload sparse_ls|rosenbrock|logreg|batched] [--n N] [--coh C] [--quadratic-ls]
 
 A "step" is one iteration of the `for n = 1:max_iters` body of minimizeobjective
 (src/engine/optim.jl:50-160): one strong-Wolfe line search (>= 1 fdf! trial) + getβ + the
 state roll + updatedir!.  The workload is BASELINE.json's metric config: sparse least squares
 ½‖Ax−b‖², CSR A 2e8×2e8 with 10 nnz/row, FP64 Hager-Zhang CG (configs[2]; it fits one B200);
-`--workload rosenbrock` runs configs[1] (extended Rosenbrock n = 1e8).  Under torchrun the rows
-/ vector slices are sharded over the ranks (total work fixed: "strong" scaling).
+`--workload rosenbrock` runs configs[1] (extended Rosenbrock n = 1e8), `logreg` configs[3] (CSR
+logistic regression 5e7 × 2e7, L-BFGS m = 10), `batched` configs[4] (262,144 independent n = 512
+problems, whole solver on the device).  Under torchrun the rows / vector slices / samples / problems
+are sharded over the ranks (total work fixed: "strong" scaling).
 
 `--impl reference` times the reference's CPU path — oracle/ (the C restatement; Julia is not
 installed here or on the GPU box) in the reference's own shape: unfused passes, allocating
@@ -292,7 +294,7 @@ def run_ours(args):
     if world > 1:
         ctx.comm_init_torch()
     n = args.n or FULL_N[args.workload]
-    K, W = args.steps, args.warmup
+    K, W = max(args.steps, 1), max(args.warmup, 3)       # timing rule: at least three warm-up steps
     obj, x0 = make_objective(cg, args, ctx, n)
     n_local = obj.n_local
     nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
