@@ -45,6 +45,7 @@ _SIGS = {
     "cgo_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "cgo_ctx_set_reduction_ctas": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_set_gather_block_bytes": (C.c_int, [_vp, C.c_int64]),
+    "cgo_ctx_set_sweep_window": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_sm_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cgo_ctx_kernel_launches": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_timing": (C.c_int, [_vp, C.c_int]),
@@ -65,6 +66,7 @@ _SIGS = {
     "cgo_obj_barrier_infeasible": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "cgo_obj_destroy": (C.c_int, [_vp]),
     "cgo_obj_dims": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cgo_obj_reduction_site": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cgo_obj_bytes_per_eval": (C.c_int, [_vp, _dp]),
     "cgo_obj_default_x0": (C.c_int, [_vp, C.c_uint64, C.c_double, _dp]),
     "cgo_obj_csr_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_HERE, "..", "include"), "-o", LIB] + sources() + ["-ldl"]
+    extra = os.environ.get("CGO_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(_HERE, "..", "include"), "-o", LIB] + sources() + ["-ldl"]
     env = dict(os.environ)
     # /opt/gcc's wrapper lacks some runtime specs; the distro compiler is the supported host cc
     if os.path.exists("/usr/bin/g++"):

@@ -312,6 +312,60 @@ struct GradCombine {
     }
 };
 
+// Dots of the gather-bound CSR objectives (csr.cu k_spmv_direct keeps no reduction): Σ r² after K_b; after K_c
+// the eight dots of EpiGrad — norm(df_xp)² (optim.jl:107), dϕ = g⁺·u (cg_utils.jl:20) and the getβ dots
+// (cg_flavours.jl:63-76, 96-105, 140-145, 164-167) — in the BLAS-1 canonical order.
+struct VecSumSq {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 4;
+    struct In { double2 a; };
+    const double2 *a;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const { return In{cgo_ld2(a + q)}; }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        acc[0] = acc[0] + in.a.x * in.a.x;
+        if (v2) acc[0] = acc[0] + in.a.y * in.a.y;
+    }
+};
+struct Dots3 {                 // {a·b, b·b, a·a}
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 3;
+    static constexpr int OCC = 4;
+    struct In { double2 a, b; };
+    const double2 *a, *b;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const { return In{cgo_ld2(a + q), cgo_ld2(b + q)}; }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        acc[0] = acc[0] + in.a.x * in.b.x; acc[1] = acc[1] + in.b.x * in.b.x; acc[2] = acc[2] + in.a.x * in.a.x;
+        if (v2) { acc[0] = acc[0] + in.a.y * in.b.y; acc[1] = acc[1] + in.b.y * in.b.y; acc[2] = acc[2] + in.a.y * in.a.y; }
+    }
+};
+struct GradDots {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 8;
+    static constexpr int OCC = 2;
+    struct In { double2 gp, g, u; };
+    const double2 *gp, *g, *u;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const { return In{cgo_ld2(gp + q), cgo_ld2(g + q), cgo_ld2(u + q)}; }
+    __device__ __forceinline__ void one(double gn, double gg, double uu, double (&acc)[K]) const {
+        const double y = gn - gg;
+        acc[CGO_P_DPHI - 1] = acc[CGO_P_DPHI - 1] + gn * uu;
+        acc[CGO_P_GPGP - 1] = acc[CGO_P_GPGP - 1] + gn * gn;
+        acc[CGO_P_YY - 1] = acc[CGO_P_YY - 1] + y * y;
+        acc[CGO_P_UY - 1] = acc[CGO_P_UY - 1] + uu * y;
+        acc[CGO_P_YGP - 1] = acc[CGO_P_YGP - 1] + y * gn;
+        acc[CGO_P_GPG - 1] = acc[CGO_P_GPG - 1] + gn * gg;
+        acc[CGO_P_UG - 1] = acc[CGO_P_UG - 1] + uu * gg;
+        acc[CGO_P_UU - 1] = acc[CGO_P_UU - 1] + uu * uu;
+    }
+    __device__ __forceinline__ void apply(int64_t, const In &in, double (&acc)[K], bool v2) const {
+        one(in.gp.x, in.g.x, in.u.x, acc);
+        if (v2) one(in.gp.y, in.g.y, in.u.y, acc);
+    }
+};
+
 // updateiteratesolvesys! (src/engine/solve_system.jl:237-253): x_next[i] = base[i] + m*df_xp[i]
 // (base = x_next itself as the reference writes it, or x for Alg. 3.1 as published)
 struct SolveSysProject {
@@ -450,6 +504,7 @@ struct RosenObj : cgo_obj {
     }
     // fused minimum: R x,g,u ; W (u,) xp, g⁺
     double bytes_per_eval() const override { return 8.0 * 5.0 * (double)n_local; }
+    void reduction_site(int32_t *V, int32_t *U) const override { *V = 2; *U = CGO_U_VEC; }
     int default_x0(uint64_t seed, double perturb, double *x0) override {
         for (int64_t i = 0; i < n_local; ++i) {
             int64_t gi = offset + i;
@@ -539,6 +594,11 @@ extern "C" int cgo_obj_dims(cgo_obj *o, int64_t *nl, int64_t *ng, int64_t *off) 
     if (nl) *nl = o->n_local;
     if (ng) *ng = o->n_global;
     if (off) *off = o->offset;
+    return 0;
+}
+extern "C" int cgo_obj_reduction_site(cgo_obj *o, int32_t *V, int32_t *U) {
+    CGO_CHECK(o && V && U, "NULL argument");
+    o->reduction_site(V, U);
     return 0;
 }
 extern "C" int cgo_obj_bytes_per_eval(cgo_obj *o, double *bytes) {
@@ -642,6 +702,7 @@ struct BarrierObj : cgo_obj {
         return 0;
     }
     double bytes_per_eval() const override { return inner->bytes_per_eval() + 8.0 * 7.0 * (double)n_local; }
+    void reduction_site(int32_t *V, int32_t *U) const override { *V = 2; *U = CGO_U_VEC; }
     int default_x0(uint64_t seed, double perturb, double *x0) override { return inner->default_x0(seed, perturb, x0); }
 };
 
@@ -870,6 +931,22 @@ int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused, double beta, const H
         return fused ? launch_axpy_dir<true, 2>(st, a, beta, push) : launch_axpy_dir<false, 2>(st, a, beta, push);
     if (push) return fused ? launch_axpy_dir<true, 1>(st, a, beta, push) : launch_axpy_dir<false, 1>(st, a, beta, push);
     return fused ? launch_axpy_dir<true, 0>(st, a, beta, nullptr) : launch_axpy_dir<false, 0>(st, a, beta, nullptr);
+}
+
+int cgo_blas1_sumsq(cgo_ctx *c, const double *a, int64_t n, int slot) {
+    VecSumSq op;
+    op.a = (const double2 *)a;
+    return launch_blas1(c, op, n, cgo_red_args(c, slot));
+}
+int cgo_blas1_dots3(cgo_ctx *c, const double *a, const double *b, int64_t n, int slot) {
+    Dots3 op;
+    op.a = (const double2 *)a; op.b = (const double2 *)b;
+    return launch_blas1(c, op, n, cgo_red_args(c, slot));
+}
+int cgo_blas1_grad_dots(cgo_state *st) {
+    GradDots op;
+    op.gp = (const double2 *)st->gp; op.g = (const double2 *)st->g; op.u = (const double2 *)st->u;
+    return launch_blas1(st->ctx, op, st->n, cgo_red_args(st->ctx, CGO_P_DPHI));
 }
 
 int cgo_blas1_grad_combine(cgo_state *st, const double *q, int nparts, int64_t stride, double invN, double lambda,

@@ -86,6 +86,9 @@ extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
     CGO_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sms = prop.multiProcessorCount;
     if (const char *e = getenv("CGO_CSR_PASS_OCC")) c->csr_pass_occ = (e[0] == '3') ? 3 : 2;
+    if (const char *e = getenv("CGO_CSR_MODE")) c->csr_mode = atoi(e);
+    if (const char *e = getenv("CGO_DIRECT_CFG")) c->direct_cfg = atoi(e);
+    if (const char *e = getenv("CGO_SWEEP_WINDOW")) c->sweep_window = atoi(e) > 0 ? atoi(e) : 0;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -95,6 +98,8 @@ extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
     CGO_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * CGO_MAXK * CGO_GMAX));
     CGO_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
     CGO_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int) * 4, c->stream));
+    CGO_CUDA(cudaMalloc(&c->d_progress, sizeof(unsigned long long) * 8));
+    CGO_CUDA(cudaMemsetAsync(c->d_progress, 0, sizeof(unsigned long long) * 8, c->stream));
     CGO_CUDA(cudaHostAlloc(&c->h_pack, sizeof(double) * CGO_PACK_LEN, cudaHostAllocMapped));
     CGO_CUDA(cudaHostGetDevicePointer(&c->d_pack_map, c->h_pack, 0));
     CGO_CUDA(cudaMalloc(&c->d_pack, sizeof(double) * CGO_PACK_LEN));
@@ -117,6 +122,7 @@ extern "C" int cgo_ctx_destroy(cgo_ctx *c) {
     cudaFree(c->d_gather_peer); cudaFree(c->d_flags_peer);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)c->comm);
     cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFreeHost(c->h_pack);
+    cudaFree(c->d_progress);
     cudaFree(c->d_pack); cudaFree(c->d_gather); cudaFree(c->d_scal);
     for (auto &kv : c->dev_pool) for (void *p : kv.second) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -145,6 +151,12 @@ extern "C" int cgo_ctx_set_gather_block_bytes(cgo_ctx *c, int64_t bytes) {
 extern "C" int cgo_ctx_sm_count(cgo_ctx *c, int *sms) {
     CGO_CHECK(c && sms, "NULL argument");
     *sms = c->sms;
+    return 0;
+}
+extern "C" int cgo_ctx_set_sweep_window(cgo_ctx *c, int tiles) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CHECK(tiles >= 0, "cgo_ctx_set_sweep_window: negative window");
+    c->sweep_window = tiles;
     return 0;
 }
 extern "C" int cgo_ctx_kernel_launches(cgo_ctx *c, int64_t *count) {

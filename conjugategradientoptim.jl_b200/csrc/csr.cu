@@ -59,6 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -147,9 +158,104 @@ __device__ __forceinline__ double ld_gather_f64_if(const double *p, uint64_t pol
     return r;
 }
 
+// run-time knobs of the sweep
+struct TsKnobs {
+    int window;                        // lockstep window in tiles per CTA (0: free-running)
+    unsigned long long *progress;      // tiles consumed by all CTAs of this launch
+};
+
+// ---------------- producer: one lane streams tiles into the ring, about three tiles ahead
+template <class L, class Epi>
+__device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, const RedArgs &red, const TsKnobs &kn,
+                                           double *s_val, int32_t *s_col, unsigned char *s_desc, uint64_t *s_full,
+                                           uint64_t *s_empty, uint32_t *s_len, int nact, int64_t ntiles) {
+    constexpr int NOPS = Epi::NOPS;
+    constexpr int RING = L::RING, CHMAX = L::CHMAX;
+    const int64_t nrows = A.nrows;
+    const uint64_t pol = l2_policy_evict_first();
+    uint32_t c = 0, tail = 0;         // chunks issued / reclaimed
+    uint32_t head = 0, nfree = RING;
+    int v = blockIdx.x;
+    int64_t tile = v;
+    bool have = true;
+    int nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
+    int64_t p0n = __ldg(A.rowptr + tile * CGO_B), p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
+    unsigned long long ktile = 0;     // own tiles issued so far
+    bool lockstep = kn.window > 0;
+    while (have) {
+        const int64_t r0 = tile * CGO_B, p0 = p0n, p1 = p1n;
+        const int nvalid = nvalid_n;
+        // Lockstep window.  Every persistent CTA sweeps its own tiles v, v+G, v+2G, …; nothing else keeps the
+        // CTAs at the same height of the matrix, and on a 2e8-row matrix they drift apart by more rows than the
+        // band is wide: the window of the gathered vector that is live then exceeds L2 and every gather becomes
+        // a DRAM sector read (measured: 86 GB of DRAM reads against 30 GB algorithmic, 36 ms instead of 15).
+        // So a CTA never runs more than `window` tiles ahead of the grid's average progress.  Needs the grid to
+        // be co-resident (it is sized to be); if the count does not move for ~4 ms the CTA stops waiting.
+        if (lockstep && ktile >= (unsigned long long)kn.window) {
+            const unsigned long long need = (ktile - (unsigned long long)kn.window) * (unsigned long long)gridDim.x;
+            unsigned int polls = 0;
+            while (*(volatile unsigned long long *)kn.progress < need) {
+                // consumed chunks are only counted when they are reclaimed: reclaim what has been released
+                while (tail < c && mbar_test(&s_empty[tail % TS_ND], (tail / TS_ND) & 1)) {
+                    nfree += s_len[tail % TS_ND] & 0x7fffffffu;
+                    if (s_len[tail % TS_ND] >> 31) atomicAdd(kn.progress, 1ULL);
+                    ++tail;
+                }
+                __nanosleep(64);
+                if (++polls > (1u << 16)) { lockstep = false; break; }
+            }
+        }
+        ++ktile;
+        have = ts_next_tile(v, tile, nact, ntiles, red.G);
+        if (have) {                   // row pointers of the next tile: in flight during this one
+            nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
+            p0n = __ldg(A.rowptr + tile * CGO_B);
+            p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
+        }
+        bool first = true;
+        for (int64_t cs = p0 & ~(int64_t)3; first || cs < p1; cs += CHMAX) {
+            const int64_t ce = cs + CHMAX < p1 ? cs + CHMAX : p1;
+            const uint32_t cnt4 = p1 > p0 ? (uint32_t)((ce - cs + 3) & ~(int64_t)3) : 0u;
+            // a free descriptor and cnt4 free ring entries: reclaim released chunks, oldest first
+            while (tail + TS_ND <= c || nfree < cnt4) {
+                mbar_wait(&s_empty[tail % TS_ND], (tail / TS_ND) & 1);
+                nfree += s_len[tail % TS_ND] & 0x7fffffffu;
+                if (lockstep && (s_len[tail % TS_ND] >> 31)) atomicAdd(kn.progress, 1ULL);
+                ++tail;
+            }
+            const int d = c % TS_ND;
+            s_len[d] = cnt4 | (cs + CHMAX >= p1 ? 0x80000000u : 0u);       // bit 31: last chunk of its tile
+            nfree -= cnt4;
+            unsigned char *desc = s_desc + d * L::DESC_BYTES;
+            const uint32_t rpb = first ? (uint32_t)((((nvalid + 1) * 8) + 15) & ~15) : 0u;
+            const uint32_t opb = first ? (uint32_t)(((nvalid * 8) + 15) & ~15) : 0u;
+            mbar_expect_tx(&s_full[d], cnt4 * 12u + rpb + NOPS * opb);
+            if (first) {
+                tma_load_1d(desc, A.rowptr + r0, rpb, &s_full[d], pol);
+#pragma unroll
+                for (int o = 0; o < NOPS; ++o)
+                    tma_load_1d(desc + L::RP_BYTES + o * L::OP_BYTES, epi.operand(o) + r0, opb, &s_full[d], pol);
+            }
+            if (cnt4) {
+                const uint32_t n1 = cnt4 < RING - head ? cnt4 : RING - head;   // up to the ring's end
+                tma_load_1d(s_val + head, A.val + cs, n1 * 8u, &s_full[d], pol);
+                tma_load_1d(s_col + head, A.col + cs, n1 * 4u, &s_full[d], pol);
+                if (n1 < cnt4) {                                               // wrapped remainder
+                    tma_load_1d(s_val, A.val + cs + n1, (cnt4 - n1) * 8u, &s_full[d], pol);
+                    tma_load_1d(s_col, A.col + cs + n1, (cnt4 - n1) * 4u, &s_full[d], pol);
+                }
+                head += cnt4;
+                if (head >= RING) head -= RING;
+            }
+            first = false;
+            ++c;
+        }
+    }
+}
+
 template <class Epi, int OCC>
 __global__ void __launch_bounds__(TS_THREADS, OCC)
-k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
+k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red, TsKnobs kn) {
     constexpr int K = Epi::K;
     constexpr int NOPS = Epi::NOPS;
     using L = TsLayout<NOPS, OCC>;
@@ -173,63 +279,8 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
     __syncthreads();
 
     if (tid >= CGO_B) {                       // ---------------- producer warp
-        if (tid == CGO_B && (int)blockIdx.x < nact) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t c = 0, tail = 0;         // chunks issued / reclaimed
-            uint32_t head = 0, nfree = RING;
-            int v = blockIdx.x;
-            int64_t tile = v;
-            bool have = true;
-            int nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
-            int64_t p0n = __ldg(A.rowptr + tile * CGO_B), p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
-            while (have) {
-                const int64_t r0 = tile * CGO_B, p0 = p0n, p1 = p1n;
-                const int nvalid = nvalid_n;
-                have = ts_next_tile(v, tile, nact, ntiles, red.G);
-                if (have) {                   // row pointers of the next tile: in flight during this one
-                    nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
-                    p0n = __ldg(A.rowptr + tile * CGO_B);
-                    p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
-                }
-                bool first = true;
-                for (int64_t cs = p0 & ~(int64_t)3; first || cs < p1; cs += CHMAX) {
-                    const int64_t ce = cs + CHMAX < p1 ? cs + CHMAX : p1;
-                    const uint32_t cnt4 = p1 > p0 ? (uint32_t)((ce - cs + 3) & ~(int64_t)3) : 0u;
-                    // a free descriptor and cnt4 free ring entries: reclaim released chunks, oldest first
-                    while (tail + TS_ND <= c || nfree < cnt4) {
-                        mbar_wait(&s_empty[tail % TS_ND], (tail / TS_ND) & 1);
-                        nfree += s_len[tail % TS_ND];
-                        ++tail;
-                    }
-                    const int d = c % TS_ND;
-                    s_len[d] = cnt4;
-                    nfree -= cnt4;
-                    unsigned char *desc = s_desc + d * L::DESC_BYTES;
-                    const uint32_t rpb = first ? (uint32_t)((((nvalid + 1) * 8) + 15) & ~15) : 0u;
-                    const uint32_t opb = first ? (uint32_t)(((nvalid * 8) + 15) & ~15) : 0u;
-                    mbar_expect_tx(&s_full[d], cnt4 * 12u + rpb + NOPS * opb);
-                    if (first) {
-                        tma_load_1d(desc, A.rowptr + r0, rpb, &s_full[d], pol);
-#pragma unroll
-                        for (int o = 0; o < NOPS; ++o)
-                            tma_load_1d(desc + L::RP_BYTES + o * L::OP_BYTES, epi.operand(o) + r0, opb, &s_full[d], pol);
-                    }
-                    if (cnt4) {
-                        const uint32_t n1 = cnt4 < RING - head ? cnt4 : RING - head;   // up to the ring's end
-                        tma_load_1d(s_val + head, A.val + cs, n1 * 8u, &s_full[d], pol);
-                        tma_load_1d(s_col + head, A.col + cs, n1 * 4u, &s_full[d], pol);
-                        if (n1 < cnt4) {                                               // wrapped remainder
-                            tma_load_1d(s_val, A.val + cs + n1, (cnt4 - n1) * 8u, &s_full[d], pol);
-                            tma_load_1d(s_col, A.col + cs + n1, (cnt4 - n1) * 4u, &s_full[d], pol);
-                        }
-                        head += cnt4;
-                        if (head >= RING) head -= RING;
-                    }
-                    first = false;
-                    ++c;
-                }
-            }
-        }
+        if (tid == CGO_B && (int)blockIdx.x < nact)
+            ts_produce<L, Epi>(A, epi, red, kn, s_val, s_col, s_desc, s_full, s_empty, s_len, nact, ntiles);
         return;
     }
 
@@ -310,10 +361,14 @@ static int launch_csr_occ(cgo_ctx *c, const CsrMat &A, const double *xg, const E
     int64_t phys = (int64_t)c->sms * OCC;
     int grid = (int)(nact < phys ? nact : phys);
     if (grid < 1) grid = 1;
+    CGO_CHECK(!A.sliced, "internal: k_csr_rows on a matrix in the sliced layout");
     const size_t smem = TsLayout<Epi::NOPS, OCC>::BYTES;
     CGO_CUDA(cudaFuncSetAttribute(k_csr_rows<Epi, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the lockstep window only matters (and only costs a memset) when a CTA sweeps many tiles
+    TsKnobs kn{ntiles > 8 * (int64_t)grid ? c->sweep_window : 0, c->d_progress};
+    if (kn.window > 0) CGO_CUDA(cudaMemsetAsync(c->d_progress, 0, sizeof(unsigned long long), c->stream));
     cgo_timer_begin(c, tclass);
-    k_csr_rows<Epi, OCC><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red);
+    k_csr_rows<Epi, OCC><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red, kn);
     cgo_timer_end(c);
     c->launches++;
     CGO_CUDA(cudaGetLastError());
@@ -522,6 +577,205 @@ static WithInit<Base> with_init(const Base &b, const double *partial) {
     static_cast<Base &>(w) = b;
     w.partial = partial;
     return w;
+}
+
+// ------------------------------------------------------------------ the gather-bound SpMV kernel
+// Matrices whose gathers do not coalesce — every lane of a warp-level gather touches its own 128-byte line: the
+// per-row-random cfg-3 matrix (coh_log2 < 4), the column-block passes of logistic regression — are bound by
+// L1TEX, one line per clock and SM: ≈ 245 G gathers/s on a B200 whatever the load path (scratch/gather_bench.cu:
+// LDG, LDG with L2 hints, TEX, LDGSTS, TMA gather4 all measured).  What reaches that ceiling is many warps with
+// a short instruction stream, each keeping a batch of gathers in flight: the prototype in gather_bench.cu gets
+// 244 G gathers/s with 32 warps per SM, against ≈ 105 G/s for k_csr_rows, whose canonical reduction order caps
+// the grid at G = 296 CTAs (16 warps per SM) and whose ring, barriers and epilogue leave those warps without a
+// gather in flight half of the time.  So for these matrices the reductions leave the SpMV:
+//   k_spmv_direct  y = A x [− b | /N + λw | + partial]: no reduction ⇒ no canonical order to respect ⇒ any
+//                  grid, any schedule; 24-32 warps per SM, values and column indices read straight from HBM by
+//                  coalesced loads (sliced layout: the k-th entries of a slice's 32 rows are consecutive), no
+//                  shared memory, tiles handed out dynamically — which also keeps all warps inside one band
+//                  of the gathered vector, so it stays L2-resident (k_csr_rows needs a lockstep window for that);
+//   k_blas1        the dots, in the BLAS-1 canonical order (V = 2, U = 4): Σ r² after K_b, the eight getβ dots
+//                  after K_c — 16n more bytes per evaluation than the fused epilogues (+5 %).
+// Each row's products are still added one by one in storage order: row sums are bit-identical to k_csr_rows'.
+constexpr int DIR_GRAB = 4;                 // slices (of 32 rows) a warp takes from the queue at a time
+struct DirArgs {
+    unsigned long long *next;               // slice queue head (reset by the last CTA)
+    unsigned int *ticket;
+    // cross-GPU hand-off, as in RedArgs
+    unsigned long long *sig0, *sig1;
+    const unsigned long long *wait0, *wait1;
+    unsigned long long sig_val, wait_val;
+    void *const *flags_all;
+    const unsigned long long *wait_all;
+    int sig_all_slot, nranks, me;
+};
+__device__ __forceinline__ int32_t ld_stream_s32_if(const int32_t *p, bool on) {
+    int32_t r = 0;
+    asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\n@q ld.global.nc.L1::no_allocate.s32 %0, [%1];\n}\n" : "+r"(r) : "l"(p), "r"((int)on));
+    return r;
+}
+__device__ __forceinline__ double ld_stream_f64_if(const double *p, bool on) {
+    double r = 0.0;
+    asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\n@q ld.global.nc.L1::no_allocate.f64 %0, [%1];\n}\n" : "+d"(r) : "l"(p), "r"((int)on));
+    return r;
+}
+
+// one batch of UN levels of a slice: the lane's entries, gathered and added in order
+template <int UN, bool UNIFORM>
+__device__ __forceinline__ double dir_batch(const CsrMat &A, const double *__restrict__ xg, uint64_t gpol, int64_t sb,
+                                            int64_t &off, int len, int k0, int lane, uint32_t lt, double sum) {
+    int32_t cj[UN];
+    double vj[UN], xj[UN];
+#pragma unroll
+    for (int j = 0; j < UN; ++j) {
+        const bool on = len > k0 + j;
+        int64_t idx;
+        if (UNIFORM) { idx = sb + off + lane; off += 32; }
+        else {
+            const uint32_t m = __ballot_sync(0xffffffffu, on);
+            idx = sb + off + __popc(m & lt);
+            off += __popc(m);
+        }
+        cj[j] = ld_stream_s32_if(A.col + idx, on);
+        vj[j] = ld_stream_f64_if(A.val + idx, on);
+    }
+#pragma unroll
+    for (int j = 0; j < UN; ++j) xj[j] = ld_gather_f64_if(xg + cj[j], gpol, len > k0 + j);
+#pragma unroll
+    for (int j = 0; j < UN; ++j) {
+        const double p = vj[j] * xj[j];
+        if (len > k0 + j) sum = sum + p;
+    }
+    return sum;
+}
+
+template <class F, int UN, int OCC>
+__global__ void __launch_bounds__(CGO_B, OCC)
+k_spmv_direct(CsrMat A, const double *__restrict__ xg, F f, DirArgs da) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t nrows = A.nrows, nslices = (nrows + 31) / 32;
+    if (da.wait0 != nullptr || da.wait_all != nullptr) {        // sharded: the peers' pushes have landed
+        if (tid == 0 && da.wait0 != nullptr) {
+            cgo_spin_until(da.wait0, da.wait_val);
+            if (da.wait1 != nullptr) cgo_spin_until(da.wait1, da.wait_val);
+        }
+        if (da.wait_all != nullptr && tid < da.nranks) cgo_spin_until(da.wait_all + tid, da.wait_val);
+        __syncthreads();
+    }
+    const uint64_t gpol = l2_policy_evict_last();
+    for (;;) {
+        unsigned long long s0 = 0;
+        if (lane == 0) s0 = atomicAdd(da.next, (unsigned long long)DIR_GRAB);
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
+        if ((int64_t)s0 >= nslices) break;
+#pragma unroll 1
+        for (int g = 0; g < DIR_GRAB; ++g) {
+            const int64_t s = (int64_t)s0 + g;
+            if (s >= nslices) break;
+            const int64_t row = s * 32 + lane;
+            const bool valid = row < nrows;
+            int64_t rp0 = 0, rp1 = 0;
+            if (valid) { rp0 = __ldg(A.rowptr + row); rp1 = __ldg(A.rowptr + row + 1); }
+            const int len = valid ? (int)(rp1 - rp0) : -1;
+            const int64_t sb = __shfl_sync(0xffffffffu, rp0, 0);
+            const int maxlen = __reduce_max_sync(0xffffffffu, len);
+            const bool uniform = __all_sync(0xffffffffu, len == maxlen);
+            double sum = valid ? f.init(row) : 0.0;
+            int64_t off = 0;
+            if (uniform) { for (int k0 = 0; k0 < maxlen; k0 += UN) sum = dir_batch<UN, true>(A, xg, gpol, sb, off, len, k0, lane, lt, sum); }
+            else { for (int k0 = 0; k0 < maxlen; k0 += UN) sum = dir_batch<UN, false>(A, xg, gpol, sb, off, len, k0, lane, lt, sum); }
+            if (valid) f.row(row, sum);
+        }
+    }
+    // the last CTA re-arms the queue and hands the pushed halos to the peers
+    __shared__ bool is_last;
+    if (da.sig0 != nullptr || da.flags_all != nullptr) __threadfence_system();
+    else __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(da.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && tid == 0) {
+        *da.ticket = 0u;
+        *da.next = 0ULL;
+        __threadfence_system();
+        if (da.sig0 != nullptr) {
+            cgo_st_release_sys(da.sig0, da.sig_val);
+            if (da.sig1 != nullptr) cgo_st_release_sys(da.sig1, da.sig_val);
+        }
+        if (da.flags_all != nullptr)
+            for (int r = 0; r < da.nranks; ++r)
+                cgo_st_release_sys((unsigned long long *)da.flags_all[r] + da.sig_all_slot + da.me, da.sig_val);
+    }
+}
+
+// row functors of k_spmv_direct: init(i) = what the row sum starts from, row(i, sum) = what to do with it
+struct DirStore {                       // y = A x
+    double *y;
+    __device__ __forceinline__ double init(int64_t) const { return 0.0; }
+    __device__ __forceinline__ void row(int64_t i, double sum) const { y[i] = sum; }
+};
+struct DirStoreInit {                   // column-block pass: y = partial + A_j x
+    double *y;
+    const double *partial;
+    __device__ __forceinline__ double init(int64_t i) const { return ld_stream_f64(partial + i); }
+    __device__ __forceinline__ void row(int64_t i, double sum) const { y[i] = sum; }
+};
+template <bool PUSH>
+struct DirResidual {                    // r = A xp − b  (+ halo push, as EpiResidualT)
+    const double *b;
+    double *r;
+    double *prev_right, *next_left;
+    int64_t halo, nrows;
+    __device__ __forceinline__ double init(int64_t) const { return 0.0; }
+    __device__ __forceinline__ void row(int64_t i, double sum) const {
+        const double rr = sum - ld_stream_f64(b + i);
+        r[i] = rr;
+        if (PUSH) {
+            if (i < halo) prev_right[i] = rr;
+            if (i >= nrows - halo) next_left[i - (nrows - halo)] = rr;
+        }
+    }
+};
+struct DirGradLS {                      // g⁺ = Aᵀ r
+    double *gp;
+    __device__ __forceinline__ double init(int64_t) const { return 0.0; }
+    __device__ __forceinline__ void row(int64_t j, double sum) const { st_stream_f64(gp + j, sum); }
+};
+
+static DirArgs dir_args(cgo_ctx *c, const RedArgs *red = nullptr) {
+    DirArgs d;
+    d.next = c->d_progress + 4;
+    d.ticket = c->d_ticket + 1;
+    d.sig0 = d.sig1 = nullptr; d.wait0 = d.wait1 = nullptr; d.sig_val = d.wait_val = 0;
+    d.flags_all = nullptr; d.wait_all = nullptr; d.sig_all_slot = -1; d.nranks = 1; d.me = 0;
+    if (red) {
+        d.sig0 = red->sig0; d.sig1 = red->sig1; d.wait0 = red->wait0; d.wait1 = red->wait1;
+        d.sig_val = red->sig_val; d.wait_val = red->wait_val;
+        d.flags_all = red->flags_all; d.wait_all = red->wait_all; d.sig_all_slot = red->sig_all_slot;
+        d.nranks = red->nranks; d.me = red->me;
+    }
+    return d;
+}
+template <class F, int UN, int OCC>
+static int launch_direct_k(cgo_ctx *c, const CsrMat &A, const double *xg, const F &f, const DirArgs &da, int tclass) {
+    const int64_t nslices = (A.nrows + 31) / 32;
+    int64_t want = (nslices + 8 * DIR_GRAB - 1) / (8 * DIR_GRAB), phys = (int64_t)c->sms * OCC;
+    int grid = (int)(want < phys ? want : phys);
+    if (grid < 1) grid = 1;
+    cgo_timer_begin(c, tclass);
+    k_spmv_direct<F, UN, OCC><<<grid, CGO_B, 0, c->stream>>>(A, xg, f, da);
+    cgo_timer_end(c);
+    c->launches++;
+    CGO_CUDA(cudaGetLastError());
+    return 0;
+}
+template <class F>
+static int launch_direct(cgo_ctx *c, const CsrMat &A, const double *xg, const F &f, const DirArgs &da, int tclass) {
+    CGO_CHECK(A.sliced, "internal: k_spmv_direct needs the sliced layout");
+    // measured at n = 2e8, coh_log2 = 0 (K_b / K_c ms): 10 gathers per batch × 4 CTAs per SM 7.5 / 9.3;
+    // 8 × 4: 8.0 / 9.1; 5 × 4: 7.7 / 9.3; 10 × 3: 7.9 / 10.5; 8 × 3: 8.8 / 9.9
+    if (c->direct_cfg == 1) return launch_direct_k<F, 8, 4>(c, A, xg, f, da, tclass);
+    return launch_direct_k<F, 10, 4>(c, A, xg, f, da, tclass);
 }
 
 // ------------------------------------------------------------------ counter-based hash
@@ -759,6 +1013,96 @@ static int csr_alloc(CsrMat &M, int64_t nrows, int64_t nnz) {
     CGO_CUDA(cudaMalloc(&M.rowptr, sizeof(int64_t) * (size_t)(nrows + 1 + CSR_PAD)));
     CGO_CUDA(cudaMalloc(&M.col, sizeof(int32_t) * (size_t)(nnz + CSR_PAD)));
     CGO_CUDA(cudaMalloc(&M.val, sizeof(double) * (size_t)(nnz + CSR_PAD)));
+    return 0;
+}
+
+// ------------------------------------------------------------------ sliced layout (setup)
+// Re-order the entries of every 32-row slice level-major (CsrMat::sliced; k_csr_rows ts_issue).  Row pointers
+// stay CSR row pointers: a slice still owns the range [rowptr[32s], rowptr[32s+32)), only the order inside it
+// changes, and each row's own entries keep their relative order.
+// one warp per slice; inverse = back to row-major
+// one warp per slice; inverse = back to row-major
+__global__ void k_slice_permute(CsrMat M, const int32_t *col_in, const double *val_in, int32_t *col_out, double *val_out,
+                                bool inverse) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x / 32);
+    for (int64_t s = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); s < nslices; s += wstride) {
+        const int64_t row = s * 32 + lane;
+        int64_t rs = 0, len = 0;
+        if (row < M.nrows) { rs = M.rowptr[row]; len = M.rowptr[row + 1] - rs; }
+        const int64_t sb = M.rowptr[s * 32];
+        int64_t off = 0;
+        for (int64_t k = 0;; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, len > k);
+            if (m == 0) break;
+            if (len > k) {
+                const int64_t lvl = sb + off + __popc(m & lt), rm = rs + k;
+                const int64_t src = inverse ? lvl : rm, dst = inverse ? rm : lvl;
+                col_out[dst] = col_in[src];
+                val_out[dst] = val_in[src];
+            }
+            off += __popc(m);
+        }
+    }
+}
+// a 1-in-64 sample of the 32-row slices of a row-major matrix: stats[0] += warp-level gathers (the k-th entries
+// of a slice's rows), stats[1] += distinct 128-byte lines of the gathered vector they touch
+__global__ void k_gather_lines(CsrMat M, unsigned long long *stats) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x / 32);
+    for (int64_t s = ((int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * 64; s < nslices; s += wstride * 64) {
+        const int64_t row = s * 32 + lane;
+        int64_t rs = 0, len = 0;
+        if (row < M.nrows) { rs = M.rowptr[row]; len = M.rowptr[row + 1] - rs; }
+        unsigned int nlev = 0, nlines = 0;
+        for (int64_t k = 0;; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, len > k);
+            if (m == 0) break;
+            if (len > k) {
+                const uint32_t same = __match_any_sync(m, M.col[rs + k] >> 4);
+                if ((same & lt) == 0) ++nlines;          // first lane of its line
+            }
+            ++nlev;
+        }
+        nlines = __reduce_add_sync(0xffffffffu, nlines);
+        if (lane == 0) { atomicAdd(stats, (unsigned long long)nlev); atomicAdd(stats + 1, (unsigned long long)nlines); }
+    }
+}
+// distinct 128-byte lines of the gathered vector one warp-level gather touches (row-major matrix, sampled)
+static int csr_gather_lines(cgo_ctx *c, const CsrMat &M, float *lines) {
+    unsigned long long *d_stats = c->d_progress + 2, h_stats[2] = {0, 0};
+    *lines = 1.0f;
+    if (M.nnz == 0) return 0;
+    CGO_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(h_stats), c->stream));
+    k_gather_lines<<<grid_for((M.nrows + 31) / 32 * 32, c->sms), 256, 0, c->stream>>>(M, d_stats);
+    CGO_CUDA(cudaGetLastError());
+    CGO_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream));
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_stats[0]) *lines = (float)((double)h_stats[1] / (double)h_stats[0]);
+    return 0;
+}
+static int csr_make_sliced(cgo_ctx *c, CsrMat &M) {
+    if (M.sliced || M.nnz == 0 || !M.col || !M.val) return 0;
+    int32_t *col2 = nullptr; double *val2 = nullptr;
+    auto body = [&]() -> int {
+        CGO_CUDA(cudaMalloc(&col2, sizeof(int32_t) * (size_t)(M.nnz + CSR_PAD)));
+        CGO_CUDA(cudaMalloc(&val2, sizeof(double) * (size_t)(M.nnz + CSR_PAD)));
+        CGO_CUDA(cudaMemsetAsync(col2 + M.nnz, 0, sizeof(int32_t) * CSR_PAD, c->stream));
+        CGO_CUDA(cudaMemsetAsync(val2 + M.nnz, 0, sizeof(double) * CSR_PAD, c->stream));
+        k_slice_permute<<<grid_for((M.nrows + 31) / 32 * 32, c->sms), 256, 0, c->stream>>>(M, M.col, M.val, col2, val2, false);
+        CGO_CUDA(cudaGetLastError());
+        CGO_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    int rc = body();
+    if (rc) { cudaFree(col2); cudaFree(val2); return rc; }
+    cudaFree(M.col); cudaFree(M.val);
+    M.col = col2; M.val = val2;
+    M.sliced = 1;
     return 0;
 }
 
@@ -1015,9 +1359,58 @@ struct CsrObj : cgo_obj {
     }
     // ∇²f u = Aᵀ(A u) along the current direction (north_star's Hessian-vector product; the reference
     // engine never calls one, src/engine/optim.jl:83-145).  `r` is scratch between trials.
+    // ---- gather-bound matrices (sliced layout): k_spmv_direct + the dots as BLAS-1 passes
+    bool direct() const { return A.sliced != 0; }
+    void reduction_site(int32_t *V, int32_t *U) const override {
+        if (direct()) { *V = 2; *U = CGO_U_VEC; } else { *V = 1; *U = 1; }
+    }
+    int eval_trial_ls_direct(cgo_state *st, double a, bool fused, double beta, double *out) {
+        const bool peer = r_is_peer && st->peer_x;
+        RedArgs fb, fc;                                                                   // flag hand-offs only
+        if (peer) {
+            const int R = ctx->nranks, me = ctx->rank, prev = (me + R - 1) % R, next = (me + 1) % R;
+            const unsigned long long e = ++ctx->epoch;
+            unsigned long long *fprev = (unsigned long long *)ctx->flags_peer[(size_t)prev];
+            unsigned long long *fnext = (unsigned long long *)ctx->flags_peer[(size_t)next];
+            const int64_t nprev = shard_len_of(prev);
+            HaloPush hp;
+            hp.prev_right = (double *)st->xpeers[st->xp_alloc][(size_t)prev] + halo + nprev;
+            hp.next_left = (double *)st->xpeers[st->xp_alloc][(size_t)next];
+            hp.sig_prev = fprev + CGO_F_XP_FROM_NEXT;
+            hp.sig_next = fnext + CGO_F_XP_FROM_PREV;
+            hp.epoch = e;
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                         // K_a + halo push
+            DirResidual<true> f1{b, r, (double *)rpeers[(size_t)prev] + halo + nprev, (double *)rpeers[(size_t)next], halo, nrows};
+            fb.wait0 = ctx->flags_local + CGO_F_XP_FROM_PREV; fb.wait1 = ctx->flags_local + CGO_F_XP_FROM_NEXT; fb.wait_val = e;
+            fb.sig0 = fprev + CGO_F_R_FROM_NEXT; fb.sig1 = fnext + CGO_F_R_FROM_PREV; fb.sig_val = e;
+            CGO_TRY(launch_direct(ctx, A, st->xp, f1, dir_args(ctx, &fb), CGO_T_SPMV));    // K_b + halo push
+            fc.wait0 = ctx->flags_local + CGO_F_R_FROM_PREV; fc.wait1 = ctx->flags_local + CGO_F_R_FROM_NEXT; fc.wait_val = e;
+        } else {
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                              // K_a
+            CGO_TRY(exchange(st->xp, st->n));
+            DirResidual<false> f1{b, r, nullptr, nullptr, 0, nrows};
+            CGO_TRY(launch_direct(ctx, A, st->xp, f1, dir_args(ctx), CGO_T_SPMV));         // K_b
+        }
+        CGO_TRY(cgo_blas1_sumsq(ctx, r, nrows, CGO_P_PHI));                               // Σ r²
+        if (!peer) CGO_TRY(exchange(r, nrows));
+        DirGradLS f2{st->gp};
+        CGO_TRY(launch_direct(ctx, AT, r, f2, peer ? dir_args(ctx, &fc) : dir_args(ctx), CGO_T_SPMVT));   // K_c
+        CGO_TRY(cgo_blas1_grad_dots(st));                                                 // dϕ, ‖g⁺‖², getβ dots
+        CGO_TRY(cgo_finish_pack(ctx, 12, out));
+        out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
+        return 0;
+    }
     int hessvec_dir(cgo_state *st, double *out) override {
         CGO_CHECK(!logreg, "the Hessian-vector product is implemented for least squares");
         CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
+        if (direct()) {
+            CGO_TRY(launch_direct(ctx, A, st->u, DirStore{r}, dir_args(ctx), CGO_T_SPMV));
+            CGO_TRY(cgo_blas1_sumsq(ctx, r, nrows, 0));                                   // u·Hu = ‖Au‖²
+            CGO_TRY(exchange(r, nrows));
+            CGO_TRY(launch_direct(ctx, AT, r, DirStore{st->hv}, dir_args(ctx), CGO_T_SPMVT));
+            CGO_TRY(cgo_blas1_dots3(ctx, st->u, st->hv, st->n, 1));                       // u·hv, hv·hv
+            return cgo_finish_pack(ctx, 3, out);
+        }
         EpiStoreSq e1{r};
         CGO_TRY(launch_csr(ctx, A, st->u, e1, cgo_red_args(ctx, 0), CGO_T_SPMV));
         CGO_TRY(exchange(r, nrows));
@@ -1034,6 +1427,11 @@ struct CsrObj : cgo_obj {
             CGO_CUDA(cudaMemsetAsync(qv, 0, sizeof(double) * (size_t)(nrows + CSR_PAD), ctx->stream));
         }
         CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
+        if (direct()) {
+            CGO_TRY(launch_direct(ctx, A, st->u, DirStore{qv}, dir_args(ctx), CGO_T_SPMV));
+            CGO_TRY(cgo_blas1_dots3(ctx, r, qv, nrows, 0));                               // r·v, v·v, r·r
+            return cgo_finish_pack(ctx, 3, out);
+        }
         EpiQuadV e1{qv, r};
         CGO_TRY(launch_csr(ctx, A, st->u, e1, cgo_red_args(ctx, 0), CGO_T_SPMV));
         return cgo_finish_pack(ctx, 3, out);
@@ -1043,6 +1441,13 @@ struct CsrObj : cgo_obj {
         CGO_TRY(cgo_blas1_axpy_dir(st, a, false, 0.0));                                   // xp = x + a u
         CGO_TRY(cgo_blas1_residual_axpy(ctx, r, qv, a, nrows, CGO_P_PHI));                // r += a v, Σ r²
         CGO_TRY(exchange(r, nrows));
+        if (direct()) {
+            CGO_TRY(launch_direct(ctx, AT, r, DirGradLS{st->gp}, dir_args(ctx), CGO_T_SPMVT));
+            CGO_TRY(cgo_blas1_grad_dots(st));
+            CGO_TRY(cgo_finish_pack(ctx, 12, out));
+            out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
+            return 0;
+        }
         EpiGrad<false> e2{st->gp, st->g, st->u, nullptr, 0.0, 0.0};
         CGO_TRY(launch_csr(ctx, AT, r, e2, cgo_red_args(ctx, CGO_P_DPHI), CGO_T_SPMVT));  // K_c
         CGO_TRY(cgo_finish_pack(ctx, 12, out));
@@ -1050,6 +1455,7 @@ struct CsrObj : cgo_obj {
         return 0;
     }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        if (!logreg && direct()) return eval_trial_ls_direct(st, a, fused, beta, out);
         if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);
         if (lr_sharded && lr_peer) {
             // the same data flow with both exchanges fused into the producing kernels: K_a stores
@@ -1115,8 +1521,9 @@ struct CsrObj : cgo_obj {
         if (lr_sharded)     // K_a 24d_loc | A_r + gather + R y W c | Aᵀ_r + gather + W part (d) | combine R parts,u,g,w W g⁺
             return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
                    8.0 * (3.0 * (double)nrows + 2.0 * (double)n_global + (8.0 + (double)ctx->nranks) * (double)n_local);
+        // (gather-bound matrices: the dots are separate BLAS-1 passes, R r | R g⁺, g, u instead of the staged u, g)
         return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
-               8.0 * (3.0 * (double)nrows + 6.0 * (double)n_local);
+               8.0 * (3.0 * (double)nrows + 6.0 * (double)n_local) + (direct() ? 8.0 * ((double)nrows + (double)n_local) : 0.0);
     }
     int default_x0(uint64_t, double, double *x0) override {
         for (int64_t i = 0; i < n_local; ++i) x0[i] = 0.0;
@@ -1186,6 +1593,12 @@ extern "C" int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n, int32
             FixedKFin fin{K, o->A.val};
             CGO_TRY(build_transpose(ctx, src, fin, nloc, o->AT));
         }
+        // offsets redrawn at least every 8 rows: no two lanes of a warp-level gather share a line ⇒ gather-bound
+        // (the rule is part of the canonical order: include/cgoptim.h; CGO_CSR_MODE = 1 / 2 forces never / always)
+        if (ctx->csr_mode == 2 || (ctx->csr_mode == 0 && coh_log2 < 4 && K > 1)) {
+            CGO_TRY(csr_make_sliced(ctx, o->A));
+            CGO_TRY(csr_make_sliced(ctx, o->AT));
+        }
         return 0;
     };
     int rc = body();
@@ -1223,6 +1636,14 @@ extern "C" int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t
         CsrSrc src{o->A.col, nnz};
         CsrFin fin{o->A.rowptr, nrows, o->A.val};
         CGO_TRY(build_transpose(ctx, src, fin, ncols, o->AT));
+        float la = 1.f, lt = 1.f;
+        CGO_TRY(csr_gather_lines(ctx, o->A, &la));
+        CGO_TRY(csr_gather_lines(ctx, o->AT, &lt));
+        o->A.lines_per_gather = la; o->AT.lines_per_gather = lt;
+        if (ctx->csr_mode == 2 || (ctx->csr_mode == 0 && la > 4.0f && lt > 4.0f && nrows >= 4096)) {
+            CGO_TRY(csr_make_sliced(ctx, o->A));
+            CGO_TRY(csr_make_sliced(ctx, o->AT));
+        }
         return 0;
     };
     int rc = body();
@@ -1340,11 +1761,25 @@ extern "C" int cgo_obj_csr_download(cgo_obj *obj, int transposed, int64_t *rowpt
     cudaStream_t s = o->ctx->stream;
     CGO_CUDA(cudaSetDevice(o->ctx->device));
     if (rowptr) CGO_CUDA(cudaMemcpyAsync(rowptr, M.rowptr, sizeof(int64_t) * (size_t)(M.nrows + 1), cudaMemcpyDeviceToHost, s));
-    if (col && M.nnz) CGO_CUDA(cudaMemcpyAsync(col, M.col, sizeof(int32_t) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
-    if (val && M.nnz) CGO_CUDA(cudaMemcpyAsync(val, M.val, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
-    if (b) CGO_CUDA(cudaMemcpyAsync(b, o->b, sizeof(double) * (size_t)o->nrows, cudaMemcpyDeviceToHost, s));
-    CGO_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    int32_t *ctmp = nullptr; double *vtmp = nullptr;          // row-major copies of a sliced matrix
+    auto body = [&]() -> int {
+        const int32_t *csrc = M.col; const double *vsrc = M.val;
+        if (M.sliced && M.nnz && (col || val)) {
+            CGO_CUDA(cudaMalloc(&ctmp, sizeof(int32_t) * (size_t)M.nnz));
+            CGO_CUDA(cudaMalloc(&vtmp, sizeof(double) * (size_t)M.nnz));
+            k_slice_permute<<<grid_for((M.nrows + 31) / 32 * 32, o->ctx->sms), 256, 0, s>>>(M, M.col, M.val, ctmp, vtmp, true);
+            CGO_CUDA(cudaGetLastError());
+            csrc = ctmp; vsrc = vtmp;
+        }
+        if (col && M.nnz) CGO_CUDA(cudaMemcpyAsync(col, csrc, sizeof(int32_t) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
+        if (val && M.nnz) CGO_CUDA(cudaMemcpyAsync(val, vsrc, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, s));
+        if (b) CGO_CUDA(cudaMemcpyAsync(b, o->b, sizeof(double) * (size_t)o->nrows, cudaMemcpyDeviceToHost, s));
+        CGO_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    };
+    int rc = body();
+    cudaFree(ctmp); cudaFree(vtmp);
+    return rc;
 }
 // y = A x (transposed: Aᵀ x) through the production kernel; single GPU (no halo)
 extern "C" int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, double *y_host) {
@@ -1361,8 +1796,12 @@ extern "C" int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, 
         CGO_CUDA(cudaMalloc(&dx, sizeof(double) * (size_t)nin));
         CGO_CUDA(cudaMalloc(&dy, sizeof(double) * (size_t)nout));
         CGO_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * (size_t)nin, cudaMemcpyHostToDevice, c->stream));
-        EpiStore es{dy};
-        CGO_TRY(launch_csr(c, M, dx, es, cgo_red_args(c, CGO_PACK_LEN - 1), transposed ? CGO_T_SPMVT : CGO_T_SPMV));
+        if (M.sliced) {
+            CGO_TRY(launch_direct(c, M, dx, DirStore{dy}, dir_args(c), transposed ? CGO_T_SPMVT : CGO_T_SPMV));
+        } else {
+            EpiStore es{dy};
+            CGO_TRY(launch_csr(c, M, dx, es, cgo_red_args(c, CGO_PACK_LEN - 1), transposed ? CGO_T_SPMVT : CGO_T_SPMV));
+        }
         CGO_CUDA(cudaMemcpyAsync(y_host, dy, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
         CGO_CUDA(cudaStreamSynchronize(c->stream));
         return 0;

@@ -74,6 +74,11 @@ struct cgo_ctx {
     size_t gather_block_bytes = (size_t)40 << 20;   // column-block size of large random gathers (csr.cu)
     int csr_pass_occ = 2;                           // CTAs per SM of the column-block passes (CGO_CSR_PASS_OCC=3 to try 3)
     int64_t launches = 0;
+    // lockstep window of the CSR sweep in tiles per CTA (csr.cu ts_produce; 0: free-running)
+    int sweep_window = 8;
+    int csr_mode = 0;        // 0: per matrix (sliced layout + k_spmv_direct when its gathers do not coalesce); 1: never; 2: always (CGO_CSR_MODE)
+    int direct_cfg = 0;      // k_spmv_direct variant (CGO_DIRECT_CFG: 0 = 10 gathers per batch, 1 = 8; 4 CTAs per SM)
+    unsigned long long *d_progress = nullptr;   // [0] tiles consumed by all CTAs of the running k_csr_rows launch; [1..3] set-up scratch; [4] k_spmv_direct's slice queue
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax
     unsigned int *d_ticket = nullptr;
@@ -168,6 +173,8 @@ struct cgo_obj {
     virtual int quad_begin(cgo_state *st, double *out_host);
     virtual int quad_accept(cgo_state *st, double a, double *out_host);
     virtual double bytes_per_eval() const = 0;
+    // canonical-order mapping (V, U) of the kernels that reduce this objective's trial dots (include/cgoptim.h)
+    virtual void reduction_site(int32_t *V, int32_t *U) const = 0;
     virtual int default_x0(uint64_t seed, double perturb, double *x0_host) = 0;
 };
 
@@ -209,6 +216,9 @@ struct HaloPush {
 };
 int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, const HaloPush *push = nullptr);
 int cgo_blas1_residual_axpy(cgo_ctx *ctx, double *r, const double *v, double a, int64_t nrows, int slot);
+int cgo_blas1_sumsq(cgo_ctx *ctx, const double *a, int64_t n, int slot);                        // Σ a²
+int cgo_blas1_dots3(cgo_ctx *ctx, const double *a, const double *b, int64_t n, int slot);       // {a·b, b·b, a·a}
+int cgo_blas1_grad_dots(cgo_state *st);     // the eight dots of EpiGrad over (g⁺, g, u) → pack slots CGO_P_DPHI…
 // sample-sharded logistic regression: g⁺ = (Σ_r q[r·stride + i]) / N + λ xp, partial gradients
 // added in rank order, fused with the dot pack of EpiGrad (slots CGO_P_DPHI .. CGO_P_UU)
 // wait_epoch != 0: spin until every rank's CGO_F_GPART flag reached it before reading q
@@ -221,4 +231,9 @@ struct CsrMat {
     int64_t *rowptr = nullptr;   // nrows + 1
     int32_t *col = nullptr;      // index into the gathered vector (may be negative: left halo)
     double *val = nullptr;
+    // sliced: inside every 32-row slice [rowptr[32s], rowptr[32s+32]) the entries are stored level-major
+    // (all first entries of the slice's rows in row order, then all second entries, …) instead of row-major
+    int32_t sliced = 0;
+    int64_t max_tile_nnz = 0;    // most entries in any 256-row tile
+    float lines_per_gather = 1.f;   // distinct 128-byte lines one warp-level gather touches (sampled at set-up)
 };

@@ -41,6 +41,10 @@ class Context:
         """Column-block size for objectives with large random gathers (0 disables blocking)."""
         check(lib().cgo_ctx_set_gather_block_bytes(self.h, int(nbytes)))
 
+    def set_sweep_window(self, tiles: int):
+        """Lockstep window of the CSR sweep in tiles per CTA (0: free-running); results do not depend on it."""
+        check(lib().cgo_ctx_set_sweep_window(self.h, int(tiles)))
+
     @property
     def stream_ptr(self) -> int:
         s = C.c_void_p()
@@ -144,6 +148,13 @@ class DeviceObjective:
         v = C.c_double()
         check(lib().cgo_obj_bytes_per_eval(self.h, C.byref(v)))
         return v.value
+
+    @property
+    def trial_site(self):
+        """(V, U) of the canonical reduction order the trial's dots follow (include/cgoptim.h)"""
+        v, u = C.c_int32(), C.c_int32()
+        check(lib().cgo_obj_reduction_site(self.h, C.byref(v), C.byref(u)))
+        return v.value, u.value
 
     def default_x0(self, seed: int = 24, perturb: float = 0.0) -> np.ndarray:
         x0 = np.empty(self.n_local)

@@ -25,6 +25,9 @@
  *   +0.0; the 256 lanes of a virtual CTA are combined by a xor-butterfly (16,8,4,2,1) inside
  *   each warp, then sequentially over the 8 warps; the min(G, ntiles) CTA partials are combined
  *   by the last-arriving block in exactly the same way (lane t takes partials t, t+256, ...).
+ *   CSR matrices whose gathers do not coalesce (the synthetic least-squares matrix with coh_log2 < 4; a host
+ *   CSR whose warp-level gathers touch more than four lines on average: cgo_obj_reduction_site tells) are
+ *   multiplied by a kernel without reductions, and their dots come from BLAS-1 passes (V=2, U=4).
  *   G defaults to 296 (= 2 persistent CTAs on each of a B200's 148 SMs, whatever the device: one
  *   sweep over the data by the whole grid) and is a property of the ctx.  With R ranks every rank
  *   reduces its contiguous shard this way; the R shard results are all-gathered and added in
@@ -89,6 +92,10 @@ int cgo_ctx_set_reduction_ctas(cgo_ctx *ctx, int G);        /* canonical-order G
  * evaluated one block per pass, so that the gathered window stays L2-resident (default 40 MiB;
  * 0 = never block).  Applies to objectives created afterwards; results are bit-identical. */
 int cgo_ctx_set_gather_block_bytes(cgo_ctx *ctx, int64_t bytes);
+/* lockstep window of the CSR sweep: a persistent CTA of the SpMV kernels never runs more than `tiles` of its
+ * own 256-row tiles ahead of the grid's average progress, so that all CTAs gather from the same L2-resident
+ * band of the vector (default 8; 0 = free-running; environment CGO_SWEEP_WINDOW).  Results do not depend on it. */
+int cgo_ctx_set_sweep_window(cgo_ctx *ctx, int tiles);
 int cgo_ctx_sm_count(cgo_ctx *ctx, int *sms);
 int cgo_ctx_kernel_launches(cgo_ctx *ctx, int64_t *count);  /* kernels launched so far */
 /* optional per-launch CUDA-event timing on the ctx stream, by kernel class:
@@ -142,6 +149,9 @@ int cgo_obj_barrier_set_t(cgo_obj *obj, double t);
 int cgo_obj_barrier_infeasible(cgo_obj *obj, const double *x_host, int64_t *count);
 int cgo_obj_destroy(cgo_obj *obj);
 int cgo_obj_dims(cgo_obj *obj, int64_t *n_local, int64_t *n_global, int64_t *offset);
+/* canonical-order mapping (V, U) of the kernels that reduce this objective's trial dots: (2, 4) when a BLAS-1
+ * kernel does (Rosenbrock, the barrier, gather-bound CSR matrices), (1, 1) for the row-per-lane CSR kernels */
+int cgo_obj_reduction_site(cgo_obj *obj, int32_t *V, int32_t *U);
 int cgo_obj_bytes_per_eval(cgo_obj *obj, double *bytes);   /* algorithmic HBM bytes of one fdf! on this rank */
 /* synthetic start / truth vectors (this rank's shard), for hosts and tests */
 int cgo_obj_default_x0(cgo_obj *obj, uint64_t seed, double perturb, double *x0_host);

@@ -326,10 +326,11 @@ static double sparse_ls_fdf(orc_objective *o, double *g, const double *x) {
 #pragma omp parallel for num_threads(o->threads) schedule(static) if (o->threads > 1)
     for (int64_t i = 0; i < o->nrows; ++i) r[i] = r[i] - o->b[i];
     double f;
-    if (o->sum_mode == ORC_SUM_CGO) {   /* K_b reduces r_i² row-per-lane: V=1, U=1 */
+    if (o->sum_mode == ORC_SUM_CGO) {   /* K_b reduces r_i² row-per-lane (V=1, U=1); for gather-bound matrices
+                                         * a BLAS-1 pass does (V=2, U=4): csr.cu k_spmv_direct */
         double *rr = o->scratch2rows;
         for (int64_t i = 0; i < o->nrows; ++i) rr[i] = r[i] * r[i];
-        f = 0.5 * orc_sum_cgo(rr, o->nrows, 1, 2);
+        f = 0.5 * (o->trial_V == 2 ? cgo_reduce(sum_term, rr, o->nrows, 2, g_blas1_U, 2) : orc_sum_cgo(rr, o->nrows, 1, 2));
     } else {
         f = 0.5 * orc_dot(r, r, o->nrows, o->sum_mode, o->threads);
     }
@@ -440,6 +441,8 @@ orc_objective *orc_obj_box_barrier(orc_objective *inner, const double *lbs, cons
 void orc_obj_barrier_set_t(orc_objective *o, double t) { o->t = t; }
 void orc_obj_set_sum_mode(orc_objective *o, int mode, int threads) { o->sum_mode = mode; if (threads > 0) o->threads = threads; }
 void orc_obj_trial_site(const orc_objective *o, int *V, int *U) { *V = o->trial_V; *U = o->trial_U; }
+/* which kernels reduce the trial's dots is a property of the device objective (cgo_obj_reduction_site) */
+void orc_obj_set_trial_site(orc_objective *o, int V, int U) { o->trial_V = V; o->trial_U = U; }
 
 /* stable counting-sort transpose: rows of Aᵀ come out sorted by source row */
 static void build_transpose(orc_objective *o) {
@@ -476,6 +479,9 @@ orc_objective *orc_obj_sparse_ls_synth(int64_t n, int32_t K, int64_t W, uint64_t
     if (K < 1 || (S > 0 && (2 * W < 2 * S || n <= 2 * W))) return NULL;
     orc_objective *o = obj_new(n, sparse_ls_fdf);
     o->trial_V = 1; o->trial_U = 1;
+    /* offsets redrawn at least every 8 rows: the device treats the matrix as gather-bound and reduces the
+     * trial's dots in BLAS-1 passes (include/cgoptim.h, canonical reduction order) */
+    if (coh_log2 < 4 && K > 1) { o->trial_V = 2; o->trial_U = 4; }
     o->threads = threads < 1 ? 1 : threads;
     o->nrows = n; o->nnz = n * (int64_t)K; o->owns = 1;
     o->rowptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));

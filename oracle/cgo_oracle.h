@@ -108,6 +108,7 @@ void orc_obj_destroy(orc_objective *);
 int64_t orc_obj_dim(const orc_objective *);
 void orc_obj_set_sum_mode(orc_objective *, int sum_mode, int threads);
 void orc_obj_trial_site(const orc_objective *, int *V, int *U);
+void orc_obj_set_trial_site(orc_objective *, int V, int U);
 void orc_set_site(int V, int U);   /* mapping used by orc_dot in ORC_SUM_CGO mode (default 2,4) */
 
 /* CSR access for cross checks (pointers owned by the objective) */

@@ -100,6 +100,7 @@ def lib():
     L.orc_set_cgo_order.argtypes = [C.c_int, C.c_int]
     L.orc_obj_set_sum_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_obj_trial_site.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_obj_set_trial_site.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_set_site.argtypes = [C.c_int, C.c_int]
     L.orc_set_cgo_lanes.argtypes = [C.c_int]
     L.orc_set_cgo_lanes.restype = None
@@ -227,6 +228,11 @@ class Objective:
         v, u = C.c_int(), C.c_int()
         lib().orc_obj_trial_site(self.h, C.byref(v), C.byref(u))
         return v.value, u.value
+
+    def set_trial_site(self, V, U):
+        """canonical-order mapping of the kernels that reduce this objective's trial dots (the device
+        objective reports its own: DeviceObjective.trial_site)"""
+        lib().orc_obj_set_trial_site(self.h, int(V), int(U))
 
     def fdf(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -72,6 +72,7 @@ def test_from_csr_ragged_bit_exact(ctx, nrows, ncols, long_row):
     rowptr, col, val, b = _ragged_csr(nrows, ncols, 5, long_row)
     obj = cg.SparseLSGPU_from_csr(nrows, ncols, rowptr, col, val, b, ctx)
     ora = O.Objective.sparse_ls_csr(nrows, ncols, rowptr, col, val, b)
+    ora.set_trial_site(*obj.trial_site)
     ora.set_sum_mode("cgo")
     rpT, ciT, vaT, _ = obj.csr(True)
     orpT, ociT, ovaT = ora.csr(True)
