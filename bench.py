@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FULL_N = {"sparse_ls": 200_000_000, "rosenbrock": 100_000_000, "logreg": 20_000_000, "batched": 512}
-SAMPLE_N = {"sparse_ls": 4_000_000, "rosenbrock": 20_000_000, "logreg": 400_000, "batched": 512}   # CPU-arm sample sizes
+SAMPLE_N = {"sparse_ls": 20_000_000, "rosenbrock": 10_000_000, "logreg": 2_000_000, "batched": 512}   # CPU arm: n/10
 LOGREG_SAMPLES_PER_FEATURE = 2.5      # cfg 4: 5e7 samples x 2e7 features, 20 nnz/row
 BATCHED_NPROB = 262_144               # cfg 5
 
@@ -46,9 +46,16 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="sparse_ls", choices=["sparse_ls", "rosenbrock", "logreg", "batched"])
     p.add_argument("--n", type=int, default=0, help="problem size (default: BASELINE.json's)")
-    p.add_argument("--coh", type=int, default=30,
-                   help="sparse_ls generator: log2 of the number of consecutive rows sharing their column "
-                        "offsets (30: ten true diagonals, SURVEY.md §8d cfg 3; 0: independent offsets per row)")
+    p.add_argument("--coh", type=int, default=0,
+                   help="sparse_ls generator: log2 of the number of consecutive rows sharing their column offsets "
+                        "(0: every row draws its own nine offsets, the banded-random matrix of SURVEY.md §8d cfg 3 — "
+                        "the headline; 30: the same offsets for all rows, i.e. ten true diagonals — reported as "
+                        "`secondary` by the default run)")
+    p.add_argument("--no-secondary", action="store_true", help="sparse_ls: skip the second matrix variant")
+    p.add_argument("--min-timed-s", type=float, default=2.0,
+                   help="repeat the K-step measurement (fresh run from x0 each time) until the timed region is this long")
+    p.add_argument("--write-fixture", action="store_true",
+                   help="N = 1: (re)write tests/golden/bench_trace_n1.json, the objective traces `parity_vs_n1` checks against")
     p.add_argument("--reduction-ctas", type=int, default=0, help="canonical-order G (0: library default)")
     p.add_argument("--quadratic-ls", action="store_true",
                    help="sparse_ls only: the quadratic-aware line search (SURVEY.md §8f N1), one SpMV + one SpMVT per iteration")
@@ -236,11 +243,15 @@ def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
     return evals * per_eval + 16.0 * n_local * iters
 
 
-def ncu_traffic(args, world, n):
+def ncu_traffic(args, world, n, coh=None):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very
-    configuration (profiles/, taken with the command in scratch/profile_r1.sh); None for any other configuration."""
+    configuration (profiles/, taken with the commands in scratch/profile_r1.sh, scratch/gpu_r2_call10.sh); None for
+    any other configuration."""
+    coh = args.coh if coh is None else coh
     name = {"sparse_ls": ("r1_ncu_full_ls_r1b.txt", 200_000_000), "rosenbrock": ("r1_ncu_full_rosen_r1.txt", 100_000_000)}
-    if world != 1 or args.workload not in name or n != name[args.workload][1] or (args.workload == "sparse_ls" and args.coh < 28):
+    if args.workload == "sparse_ls" and coh == 0:
+        name["sparse_ls"] = ("r2_ncu_full_sparse_ls_coh0_n2e8_k_spmv_direct.txt", 200_000_000)
+    if world != 1 or args.workload not in name or n != name[args.workload][1] or (args.workload == "sparse_ls" and 0 < coh < 28):
         return None, None
     path = os.path.join(ROOT, "profiles", name[args.workload][0])
     try:
@@ -274,6 +285,171 @@ def logreg_bytes(args, d_loc, nnz_loc):
     return pair + 24.0 * d_loc + 8.0 * d_loc * (world + 4), pair
 
 
+FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_trace_n1.json")
+
+
+def workload_text(args, n, coh):
+    if args.workload == "sparse_ls":
+        return (f"sparse least-squares 0.5||Ax-b||^2, CSR {n}x{n}, 10 nnz/row (banded, |col-row| < 2^20, seed 24, coh_log2={coh}: "
+                + ("the same nine offsets for all rows = ten diagonals" if coh >= 28 else
+                   ("every row draws its own nine offsets (banded-random, SURVEY.md §8d cfg 3)" if coh == 0 else
+                    "offsets redrawn every 2^%d rows" % coh))
+                + "), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)")
+    if args.workload == "logreg":
+        return (f"CSR logistic regression {int(n * LOGREG_SAMPLES_PER_FEATURE)} samples x {n} features, "
+                f"20 nnz/row, lambda 1e-6, L-BFGS m=10 + StrongWolfeBisection(1e-4,0.9)")
+    return f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
+
+
+def fixture_key(args, n, coh):
+    return f"{args.workload}/n={n}" + (f"/coh={coh}" if args.workload == "sparse_ls" else "") + \
+        ("/quadratic" if args.quadratic_ls else "")
+
+
+def parity_vs_n1(args, n, coh, trace):
+    """max relative difference between this run's objective trace (iterations 1…) and the committed N = 1 trace of
+    the same configuration (tests/golden/bench_trace_n1.json): the driver-visible 1-vs-N check of SURVEY.md §4 vi."""
+    try:
+        with open(FIXTURE) as f:
+            ref = json.load(f)["traces"].get(fixture_key(args, n, coh))
+    except (OSError, ValueError, KeyError):
+        ref = None
+    if not ref:
+        return None, "no fixture for this configuration"
+    ref = np.array([float.fromhex(v) for v in ref])
+    k = min(len(ref), len(trace))
+    if k == 0:
+        return None, "empty trace"
+    rel = np.abs(np.asarray(trace[:k]) - ref[:k]) / np.abs(ref[:k])
+    return float(rel.max()), f"first {k} iterations"
+
+
+def measure_device(cg, torch, args, ctx, obj, x0, n, coh, world, rank, local_rank, stream, barrier):
+    """Device-resident throughput of one configuration: W untimed iterations, then EXACTLY K timed ones (CUDA
+    events on the ctx stream), repeated from x0 until the timed region is at least --min-timed-s long; `ms` is
+    the mean over the repetitions.  The metric is iterations/s with ϵ out of reach, so a run only ends when the
+    line search hits the FP64 floor of the objective (≈53 iterations on cfg 3, ≈28 on cfg 4: both problems are
+    well conditioned).  If that happens inside a repetition, the clock stops at the end of the last completed
+    iteration (the 100-trial zoom that fails is not an iteration and is not timed) and a fresh run continues the
+    count from x0.  With W + K <= 50 this never triggers on cfg 3."""
+    K, W = max(args.steps, 1), max(args.warmup, 3)       # timing rule: at least three warm-up steps
+    cfg, ls = solver_configs(cg, W + K + 1, args.workload)
+    qkw = {"quadratic_linesearch": True} if (args.quadratic_ls and args.workload == "sparse_ls") else {}
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # polling runs through the warm-up; only the timed window is reported
+    reps, ms_tot, wall_tot, evals, launches, restarts, life, trace_f = 0, 0.0, 0.0, 0, 0, 0, None, None
+    timers_tot = {}
+    ctx.timing(True)
+    ctx.timing_read(reset=True)
+    first = True
+    while True:
+        run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
+        ctx.timing(False)
+        for _ in range(W):
+            assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
+        ctx.timing(True)
+        ctx.timing_read(reset=True)
+        barrier()
+        if first:
+            sampler.mark_begin()
+            first = False
+        done, ms = 0, 0.0
+        while done < K:
+            e0 = torch.cuda.Event(enable_timing=True)
+            t0 = t1 = time.perf_counter()
+            e0.record(stream)
+            e1 = e0
+            ended = False
+            l0 = l1 = ctx.kernel_launches
+            while done < K:
+                if run.step() is not None:      # line search at the FP64 floor: that step is not timed
+                    ended = True
+                    break
+                done += 1
+                evals += int(run.fdf_evals_ran)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(stream)
+                t1 = time.perf_counter()
+                l1 = ctx.kernel_launches
+            torch.cuda.synchronize()
+            launches += l1 - l0
+            wall_tot += (t1 - t0) * 1e3
+            if e1 is not e0:
+                ms += e0.elapsed_time(e1)
+            if trace_f is None:
+                trace_f = run.ret.trace.objective[:max(run.n - 1, 0)].copy()
+            if ended and done < K:
+                assert run.ret.iters_ran > 0, f"restarted run made no progress: {run.ret.status}"
+                life = run.ret.iters_ran if life is None else min(life, run.ret.iters_ran)
+                run.info.close()
+                run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
+                restarts += 1
+        for k, v in ctx.timing_read(reset=True).items():
+            a = timers_tot.setdefault(k, [0.0, 0])
+            a[0] += v[0]; a[1] += v[1]
+        run.info.close()
+        reps += 1
+        # every rank repeats the same number of times: decide on the slowest rank's clock
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_tot += float(tms.item())
+        if ms_tot * 1e-3 >= args.min_timed_s or reps >= 12:
+            break
+    sampler.mark_end()
+    barrier()
+    ctx.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    return {"K": K, "W": W, "reps": reps, "ms": ms_tot / reps, "timed_region_s": ms_tot * 1e-3, "wall_ms": wall_tot / reps,
+            "evals": evals / reps, "evals_total": evals, "launches": launches / reps, "restarts": restarts, "life": life,
+            "trace": trace_f, "timers": {k: (v[0] / reps, v[1] / reps) for k, v in timers_tot.items()}, "clocks": clocks,
+            "qkw": qkw}
+
+
+def roofline_of(args, obj, m, n, coh, world, n_local, nnz_local):
+    """dominant-kernel roofline (CUDA events on the launching stream, inside the timed region)"""
+    peak, peak_src = peaks()
+    timers, evals, K, ms = m["timers"], m["evals"], m["K"], m["ms"]
+    dom_per_eval = 2          # launches of the dominant kernel per fdf! (K_b + K_c)
+    if args.workload == "rosenbrock":
+        dom = "k_blas1<RosenTrial> (fused trial: xp, f, g+, every dot)"
+        dom_per_eval = 1
+        dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
+        dom_ms, dom_cnt = timers["trial"]
+    elif args.workload == "logreg":
+        dom = ("k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack), one pass per "
+               "L2-sized column block of the gathered vector")
+        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
+        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
+        n_evals = timers["axpy"][1]          # one K_a per fdf!; K_b / K_c may take several column-block passes
+        dom_bytes = n_evals * logreg_bytes(args, n_local, nnz_local)[1]
+        dom_per_eval = dom_cnt / max(n_evals, 1)
+    else:
+        direct = obj.trial_site == (2, 4)     # gather-bound matrix: k_spmv_direct, the dots are BLAS-1 passes
+        dom = ("k_spmv_direct (K_b: r = A xp - b; K_c: g+ = A^T r; sliced layout, no reductions)" if direct else
+               "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)")
+        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
+        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
+        # per launch pair: 2 x matrix stream + (gather 8n + R b 8n + W r 8n) + (gather 8n + W g+ 8n [+ R u,g 16n fused epilogue])
+        dom_bytes = (dom_cnt / 2.0) * (2 * matrix_bytes(n_local, nnz_local) + (40.0 if direct else 56.0) * n_local)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(args, world, n, coh)
+    total_bytes = algorithmic_bytes(args, n_local, nnz_local, evals, K)
+    if args.workload == "sparse_ls" and obj.trial_site == (2, 4):
+        total_bytes += 16.0 * n_local * evals                          # Σ r² and the eight dots as separate passes
+    return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": round(dom_bytes / max(dom_cnt, 1), 1), "peak_source": peak_src,
+            "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
+            "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+            "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
+            "whole_iteration_frac": round(total_bytes / (ms * 1e-3) / 1e9 / peak, 4),
+            "kernel_share_of_step": round((dom_ms / max(dom_cnt, 1)) * dom_per_eval * evals / ms, 4),
+            "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}}
+
+
 def run_ours(args):
     import torch
     import cgoptim_b200 as cg
@@ -294,13 +470,6 @@ def run_ours(args):
     if world > 1:
         ctx.comm_init_torch()
     n = args.n or FULL_N[args.workload]
-    K, W = max(args.steps, 1), max(args.warmup, 3)       # timing rule: at least three warm-up steps
-    obj, x0 = make_objective(cg, args, ctx, n)
-    n_local = obj.n_local
-    nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
-    if args.workload == "logreg":
-        nnz_local = 20 * shard_len(int(n * LOGREG_SAMPLES_PER_FEATURE), world, rank)
-    cfg, ls = solver_configs(cg, W + K + 1, args.workload)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -309,107 +478,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    # The metric is iterations/s with ϵ out of reach, so a run only ends when the line search hits
-    # the FP64 floor of the objective (≈53 iterations on cfg 3, ≈28 on cfg 4: both problems are
-    # well conditioned).  When that happens inside the timed region, the clock stops at the end of
-    # the last completed iteration (the 100-trial zoom that fails is not an iteration and is not
-    # timed) and a fresh run is started from x0 (state allocation and the f/g evaluation at x0 are
-    # set-up, as for the first run).  With the default K + W <= 50 this never triggers on cfg 3.
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # polling runs through the warm-up; only the timed window is reported
-    qkw = {"quadratic_linesearch": True} if (args.quadratic_ls and args.workload == "sparse_ls") else {}
-    run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
-    for _ in range(W):
-        assert run.step() is None, f"run ended during warm-up: {run.ret.status}"
-    ctx.timing(True)
-    ctx.timing_read(reset=True)
-    barrier()
-    sampler.mark_begin()
-    launches = 0
-    ms, wall_ms, evals, done, restarts, life = 0.0, 0.0, 0, 0, 0, None
-    trace_f = None
-    while done < K:
-        e0 = torch.cuda.Event(enable_timing=True)
-        t0 = t1 = time.perf_counter()
-        e0.record(stream)
-        e1 = e0
-        ended = False
-        l0 = l1 = ctx.kernel_launches
-        while done < K:
-            if run.step() is not None:      # line search at the FP64 floor: that step is not timed
-                ended = True
-                break
-            done += 1
-            evals += int(run.fdf_evals_ran)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record(stream)
-            t1 = time.perf_counter()
-            l1 = ctx.kernel_launches
-        torch.cuda.synchronize()
-        launches += l1 - l0
-        wall_ms += (t1 - t0) * 1e3
-        if e1 is not e0:
-            ms += e0.elapsed_time(e1)
-        if trace_f is None:
-            trace_f = run.ret.trace.objective[:max(run.n - 1, 0)].copy()
-        if ended and done < K:
-            assert run.ret.iters_ran > 0, f"restarted run made no progress: {run.ret.status}"
-            life = run.ret.iters_ran if life is None else min(life, run.ret.iters_ran)
-            run.info.close()
-            run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
-            restarts += 1
-    sampler.mark_end()
-    barrier()
-    timers = ctx.timing_read(reset=True)
-    ctx.timing(False)
-    clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    run.info.close()
+    obj, x0 = make_objective(cg, args, ctx, n)
+    n_local = obj.n_local
+    nnz_local = 10 * n_local if args.workload == "sparse_ls" else 0
+    if args.workload == "logreg":
+        nnz_local = 20 * shard_len(int(n * LOGREG_SAMPLES_PER_FEATURE), world, rank)
+    coh = args.coh
 
-    # dominant kernel roofline (CUDA events on the launching stream, inside the timed region)
-    peak, peak_src = peaks()
-    dom_per_eval = 2          # launches of the dominant kernel per fdf! (K_b + K_c)
-    if args.workload == "rosenbrock":
-        dom = "trial"
-        dom_per_eval = 1
-        dom_bytes = algorithmic_bytes(args, n_local, 0, evals, K)      # all bytes are trial-kernel bytes
-        dom_ms, dom_cnt = timers["trial"]
-    elif args.workload == "logreg":
-        dom = ("k_csr_rows (K_b: margins + loss; K_c: g+ = A^T c / N + lambda w + dot pack), one pass per "
-               "L2-sized column block of the gathered vector")
-        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
-        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
-        n_evals = timers["axpy"][1]          # one K_a per fdf!; K_b / K_c may take several column-block passes
-        dom_bytes = n_evals * logreg_bytes(args, n_local, nnz_local)[1]
-        dom_per_eval = dom_cnt / max(n_evals, 1)
-    else:
-        dom = "k_csr_rows (K_b: r = A xp - b; K_c: g+ = A^T r + dot pack)"
-        dom_ms = timers["spmv"][0] + timers["spmvT"][0]
-        dom_cnt = timers["spmv"][1] + timers["spmvT"][1]
-        # per launch pair: 2 x matrix stream + (gather 8n + R b 8n + W r 8n) + (gather 8n + R u,g 16n + W g+ 8n)
-        dom_bytes = (dom_cnt / 2.0) * (2 * matrix_bytes(n_local, nnz_local) + 56.0 * n_local)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic, traffic_src = ncu_traffic(args, world, n)
-    total_bytes = algorithmic_bytes(args, n_local, nnz_local, evals, K)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": round(dom_bytes / max(dom_cnt, 1), 1), "peak_source": peak_src,
-                "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
-                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
-                "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
-                "kernel_share_of_step": round((dom_ms / max(dom_cnt, 1)) * dom_per_eval * evals / ms, 4),
-                "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}}
+    # ---------------- device-resident throughput (`value`) ----------------
+    m = measure_device(cg, torch, args, ctx, obj, x0, n, coh, world, rank, local_rank, stream, barrier)
+    K, W, ms, qkw, life = m["K"], m["W"], m["ms"], m["qkw"], m["life"]
+    roofline = roofline_of(args, obj, m, n, coh, world, n_local, nnz_local)
+    par, par_note = parity_vs_n1(args, n, coh, m["trace"])
 
     # ---------------- end-to-end through the public API (`e2e`) ----------------
     e2e = None
     if not args.no_e2e:
-        cfg2, ls2 = solver_configs(cg, K, args.workload)
         x0p = torch.from_numpy(x0.copy()).pin_memory().numpy()
         # one untimed call first: page-locks the result buffers (they are pooled and reused) and
         # warms the allocator, as a long-running host would have done
@@ -440,6 +524,30 @@ def run_ours(args):
                "includes": "x0 H2D from pinned host memory, f/g at x0, K iterations (scalar pack D2H "
                            "every launch), minimizer+gradient D2H", "wall_s": round(dt, 4)}
 
+    # ---------------- the other matrix variant of cfg 3, same run (`secondary`) ----------------
+    secondary = None
+    if args.workload == "sparse_ls" and not args.no_secondary:
+        coh2 = 30 if coh < 28 else 0
+        obj.close()
+        del obj
+        args2 = argparse.Namespace(**vars(args))
+        args2.coh = coh2
+        obj2, x02 = make_objective(cg, args2, ctx, n)
+        m2 = measure_device(cg, torch, args2, ctx, obj2, x02, n, coh2, world, rank, local_rank, stream, barrier)
+        r2 = roofline_of(args2, obj2, m2, n, coh2, world, n_local, nnz_local)
+        p2, p2_note = parity_vs_n1(args2, n, coh2, m2["trace"])
+        secondary = {("coh%d" % coh2): {
+            "workload": workload_text(args2, n, coh2), "value": round(m2["K"] / (m2["ms"] * 1e-3), 4), "unit": "iterations/s",
+            "ms_per_step": round(m2["ms"] / m2["K"], 4), "repetitions": m2["reps"], "timed_region_s": round(m2["timed_region_s"], 3),
+            "fdf_evals_per_repetition": m2["evals"], "roofline": r2, "clocks": m2["clocks"],
+            "parity_vs_n1": p2, "parity_vs_n1_note": p2_note,
+            "objective_trace_head": [float(v) for v in m2["trace"][:4]]}}
+        if args.write_fixture and world == 1:
+            write_fixture(args2, n, coh2, m2["trace"])
+        obj2.close()
+    if args.write_fixture and world == 1:
+        write_fixture(args, n, coh, m["trace"])
+
     line = None
     if rank == 0:
         line = {
@@ -448,24 +556,33 @@ def run_ours(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": (f"sparse least-squares 0.5||Ax-b||^2, CSR {n}x{n}, 10 nnz/row (banded, |col-row| < 2^20, "
-                                    f"seed 24, coh_log2={args.coh}: "
-                                    + ("ten diagonals" if args.coh >= 28 else "offsets redrawn every 2^%d rows" % args.coh)
-                                    + "), Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"
-                                    if args.workload == "sparse_ls" else
-                                    f"CSR logistic regression {int(n * LOGREG_SAMPLES_PER_FEATURE)} samples x {n} features, "
-                                    f"20 nnz/row, lambda 1e-6, L-BFGS m=10 + StrongWolfeBisection(1e-4,0.9)"
-                                    if args.workload == "logreg" else
-                                    f"extended Rosenbrock n={n}, Hager-Zhang CG + StrongWolfeBisection(1e-5,0.8)"),
+            "config": {"workload": workload_text(args, n, coh),
                        "n": n, "sharding": f"rows/vector slices over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (vectors are 8n bytes >> 126 MB)",
-                       "fdf_evals_in_timed_region": evals, "restarts_in_timed_region": restarts,
-                       "quadratic_aware_linesearch": bool(qkw), "host": "python/ctypes over the C ABI"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "host_wall_ms_per_step": round(wall_ms / K, 4),
-            "objective_trace_head": [float(v) for v in trace_f[:4]],
+                       "repetitions": m["reps"], "timed_region_s": round(m["timed_region_s"], 3),
+                       "fdf_evals_in_timed_region": m["evals_total"], "restarts_in_timed_region": m["restarts"],
+                       "quadratic_aware_linesearch": bool(qkw), "host": "python/ctypes over the C ABI",
+                       "value_is": ("coh_log2=%d; the other matrix variant of cfg 3 is under `secondary`" % coh)
+                       if args.workload == "sparse_ls" else "the only variant"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(round(m["launches"])), "clocks": m["clocks"],
+            "host_wall_ms_per_step": round(m["wall_ms"] / K, 4),
+            "parity_vs_n1": par, "parity_vs_n1_note": par_note,
+            "objective_trace_head": [float(v) for v in m["trace"][:4]],
+            "secondary": secondary,
         }
     return line, ctx
+
+
+def write_fixture(args, n, coh, trace):
+    try:
+        with open(FIXTURE) as f:
+            data = json.load(f)
+    except (OSError, ValueError):
+        data = {"generator": "python bench.py --gpus 1 --write-fixture (on a B200)", "traces": {}}
+    data["traces"][fixture_key(args, n, coh)] = [float(v).hex() for v in trace]
+    os.makedirs(os.path.dirname(FIXTURE), exist_ok=True)
+    with open(FIXTURE, "w") as f:
+        json.dump(data, f, indent=0)
 
 
 # ------------------------------------------------------------------------------ batched (cfg 5)
@@ -552,8 +669,15 @@ def run_batched(args):
 
 
 # ------------------------------------------------------------------------------ CPU arm
+CPU_ITERS = 10          # iterations the CPU arm times (both in the main line's cpu_baseline and in --impl reference)
+
+
 def run_cpu(args, steps, warmup, threads):
-    """The reference's CPU path (oracle restatement, reference-shaped) on a bounded sample."""
+    """The reference's CPU path on the host cores: the oracle's C restatement in the reference's
+    own shape — unfused passes, allocating getβ, sequential sums (src/cg_utils.jl:13-20, src/cg_flavours.jl:96-105,
+    src/engine/optim.jl:136-140) — at n/10 of the full size with linear extrapolation (flagged), in two rows:
+    1 thread (Julia's own loops are single-threaded) and all cores (OpenMP on fdf! and dot/norm, emulating a
+    threaded OpenBLAS).  The same `steps` in the main line's cpu_baseline and in the --impl reference arm."""
     from oracle import oracle as O
     n_full = args.n or FULL_N[args.workload]
     n = min(SAMPLE_N[args.workload], n_full)
@@ -566,25 +690,35 @@ def run_cpu(args, steps, warmup, threads):
     else:
         obj = O.Objective.sparse_ls(n, 10, min(1 << 20, (n - 1) // 2), 24, args.coh, threads)
         x0 = np.zeros(n)
-    if args.workload == "logreg":
-        mk = lambda it: O.make_config("LBFGS", "StrongWolfeBisection", eps=1e-300, max_iters=it, lbfgs_m=10,
-                                      c1=1e-4, c2=0.9, sum_mode="seq", threads=threads)
-    else:
-        mk = lambda it: O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-300, max_iters=it,
-                                      sum_mode="seq", beta_form="literal", threads=threads)
-    if warmup:
-        O.minimize(obj, x0, mk(warmup), trace=False)
-    t0 = time.perf_counter()
-    r = O.minimize(obj, x0, mk(steps))
-    dt = time.perf_counter() - t0
-    its = r.iters_ran
-    # one fdf! at x0 is inside the timed call, as in minimizeobjective
-    rate_sample = its / dt
-    return {"value": rate_sample * (n / n_full), "unit": "iterations/s", "cores": threads, "kind": "port",
+
+    def mk(it, th):
+        if args.workload == "logreg":
+            return O.make_config("LBFGS", "StrongWolfeBisection", eps=1e-300, max_iters=it, lbfgs_m=10,
+                                 c1=1e-4, c2=0.9, sum_mode="seq", threads=th)
+        return O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-300, max_iters=it,
+                             sum_mode="seq", beta_form="literal", threads=th)
+
+    rows = []
+    for th, its in ((threads, steps), (1, max(2, steps // 3))):
+        if th == 1 and threads == 1 and rows:
+            break
+        obj.set_sum_mode("seq", th)
+        if warmup and th == threads:
+            O.minimize(obj, x0, mk(warmup, th), trace=False)
+        t0 = time.perf_counter()
+        r = O.minimize(obj, x0, mk(its, th))       # one fdf! at x0 is inside the timed call, as in minimizeobjective
+        dt = time.perf_counter() - t0
+        rows.append({"threads": th, "iterations": int(r.iters_ran), "seconds": round(dt, 3),
+                     "sample_iterations_per_s": r.iters_ran / dt, "value": r.iters_ran / dt * (n / n_full)})
+    best = rows[0]
+    return {"value": best["value"], "unit": "iterations/s", "cores": threads, "kind": "port",
             "sample": (f"oracle C restatement of the reference (Julia not installed: 'julia thread count' n/a), "
-                       f"reference-shaped arithmetic, {its} iterations at n={n} in {dt:.2f}s = {rate_sample:.3f} it/s, "
-                       f"scaled linearly by n/n_full = {n}/{n_full}; OpenMP threads on fdf! and dot/norm = {threads}"),
-            "sample_n": n, "sample_iterations_per_s": rate_sample, "host_cores": os.cpu_count()}
+                       f"reference-shaped arithmetic, {best['iterations']} iterations at n={n} (= n_full/{n_full // n}, "
+                       f"BASELINE.md §3) in {best['seconds']:.2f}s = {best['sample_iterations_per_s']:.3f} it/s, "
+                       f"scaled linearly by n/n_full = {n}/{n_full}; OpenMP threads on fdf! and dot/norm = {threads}; "
+                       f"1-thread row: {rows[-1]['value']:.5f} it/s"),
+            "sample_n": n, "extrapolated": n != n_full, "sample_iterations_per_s": best["sample_iterations_per_s"],
+            "single_thread": rows[-1] if rows[-1]["threads"] == 1 else None, "rows": rows, "host_cores": os.cpu_count()}
 
 
 def main():
@@ -594,13 +728,14 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        cb = run_cpu(args, max(args.steps, 1), min(args.warmup, 1), threads)
+        cb = run_cpu(args, CPU_ITERS, 0, threads)
         n = args.n or FULL_N[args.workload]
         line = {"impl": "reference", "metric": "lbfgs_iterations_per_s" if args.workload == "logreg" else "cg_iterations_per_s", "value": round(cb["value"], 6),
                 "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(1e3 / cb["value"], 3), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "n": n, "sample_n": cb["sample_n"]},
+                "config": {"workload": workload_text(args, n, args.coh), "n": n, "sample_n": cb["sample_n"],
+                           "cpu_iterations_timed": CPU_ITERS, "extrapolated_from_sample": cb["extrapolated"]},
                 "cpu_baseline": cb,
                 "e2e": {"value": round(cb["value"], 6), "unit": "iterations/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
@@ -610,7 +745,7 @@ def main():
     if rank == 0:
         world = int(os.environ.get("WORLD_SIZE", "1"))
         if world == 1 and not args.no_cpu_baseline and args.workload != "batched":
-            line["cpu_baseline"] = run_cpu(args, 5, 0, os.cpu_count() or 1)
+            line["cpu_baseline"] = run_cpu(args, CPU_ITERS, 0, os.cpu_count() or 1)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -51,7 +51,7 @@ function RosenbrockGPU(n::Integer, ctx::Context)
     return _wrap(ctx, h[])
 end
 "½‖Ax − b‖², synthetic banded CSR (cfg 3), or from a host CSR (0-based int64 rowptr, int32 col)."
-function SparseLSGPU(n::Integer, ctx::Context; nnz_per_row = 10, W = min(1 << 20, (n - 1) ÷ 2), seed = 24, coh_log2 = 30)
+function SparseLSGPU(n::Integer, ctx::Context; nnz_per_row = 10, W = min(1 << 20, (n - 1) ÷ 2), seed = 24, coh_log2 = 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:cgo_obj_sparse_ls_create_synthetic, LIBCGOPTIM[]), Cint,
         (Ptr{Cvoid}, Int64, Int32, Int64, UInt64, Int32, Ref{Ptr{Cvoid}}), ctx.h, n, nnz_per_row, W, seed, coh_log2, h))

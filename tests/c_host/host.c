@@ -10,7 +10,7 @@
  * src/linesearch/nocedal.jl:33-209, getβ(HagerZhang) src/cg_flavours.jl:87-108, updatetrace!
  * src/types.jl:56-71.
  *
- *   host <libcgoptim.so> <n> <max_iters> [expected.txt]
+ *   host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [x0 perturbation, default 0]
  *
  * prints one line per recorded iteration:  k  f  ‖g‖  a*  evals   (hex floats), then "status <sym> iters <n>".
  * With expected.txt (same line format, written by tests/test_gpu_c_host.py from tests/golden/traces.json)
@@ -154,19 +154,21 @@ static double beta_hager_zhang(const double *P) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 4) { fprintf(stderr, "usage: host <libcgoptim.so> <n> <max_iters> [expected.txt]\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [perturb]\n"); return 2; }
     load(argv[1]);
     const int64_t n = atoll(argv[2]);
     const long max_iters = atol(argv[3]);
-    FILE *expf = argc > 4 ? fopen(argv[4], "r") : NULL;
-    if (argc > 4 && !expf) { fprintf(stderr, "cannot open %s\n", argv[4]); return 2; }
+    const int want_exp = argc > 4 && strcmp(argv[4], "-") != 0;
+    FILE *expf = want_exp ? fopen(argv[4], "r") : NULL;
+    if (want_exp && !expf) { fprintf(stderr, "cannot open %s\n", argv[4]); return 2; }
+    const double perturb = argc > 5 ? atof(argv[5]) : 0.0;      /* SURVEY.md §8d cfg 1: x0 = (−1.2, 1, −1.2, 1, …) */
     const double eps = 1e-5;                                   /* examples/min.jl:16-35 */
     const strong_wolfe lsc = {1e-5, 0.8, 2.0, 1000, 100};
     cgo_ctx *ctx; cgo_obj *obj;
     CHECK(p_cgo_ctx_create(0, NULL, &ctx));
     CHECK(p_cgo_obj_rosenbrock_create(ctx, n, &obj));
     double *x0 = malloc(sizeof(double) * (size_t)n), *xm = malloc(sizeof(double) * (size_t)n), *gm = malloc(sizeof(double) * (size_t)n);
-    CHECK(p_cgo_obj_default_x0(obj, 24, 0.1, x0));
+    CHECK(p_cgo_obj_default_x0(obj, 24, perturb, x0));
     workspace w;
     memset(&w, 0, sizeof(w));
     CHECK(p_cgo_state_create(ctx, obj, x0, 0, &w.st, w.pack));              /* optim.jl:20-26 */

@@ -57,6 +57,40 @@ def main():
             obj = cg.SparseLSGPU(n, 10, 2048, 24, coh, ctx)
             check(f"sparse_ls coh={coh}", obj, np.zeros(n), O.Objective.sparse_ls(n, 10, 2048, 24, coh), flavour, 60)
             obj.close()
+    # SURVEY.md §8f N1 and north_star's Hessian-vector product, sharded: hv = Aᵀ(A u) and u·Hu against scipy on the
+    # oracle's global CSR; the quadratic-aware line search must take the plain path's decisions on the same ranks
+    import scipy.sparse as sp
+    for coh in (0, 30):
+        obj = cg.SparseLSGPU(n, 10, 2048, 24, coh, ctx)
+        lo, hi = obj.offset, obj.offset + obj.n_local
+        ora_obj = O.Objective.sparse_ls(n, 10, 2048, 24, coh)
+        rp, ci, va = ora_obj.csr(False)
+        A = sp.csr_matrix((va, ci, rp), shape=(n, n))
+        xr = np.random.default_rng(5).standard_normal(n)
+        ws = obj.make_workspace(xr[lo:hi], fuse_direction=False)
+        ws.reset_direction()                               # u = −g
+        g_loc = ws.download()[1]
+        uHu, hv = ws.hessvec_dir()
+        g_full = A.T @ (A @ xr - ora_obj.rhs())
+        ref = A.T @ (A @ (-g_full))
+        ok = (np.allclose(g_loc, g_full[lo:hi], rtol=1e-12, atol=1e-12 * np.max(np.abs(g_full)))
+              and np.allclose(hv, ref[lo:hi], rtol=1e-12, atol=1e-12 * np.max(np.abs(ref)))
+              and abs(uHu - (-g_full) @ ref) <= 1e-12 * abs(uHu))
+        ws.close()
+        if not ok:
+            fails.append(f"hessvec coh={coh}: rank {rank} uHu {uHu!r} vs {(-g_full) @ ref!r}")
+        _, cfg, ls = make_pair("HagerZhang", max_iters=40, eps=1e-9)
+        plain = cg.minimizeobjective(obj, np.zeros(hi - lo), cfg, ls)
+        quad = cg.minimizeobjective(obj, np.zeros(hi - lo), cfg, ls, quadratic_linesearch=True)
+        k = min(len(plain.trace.objective), len(quad.trace.objective), 30)
+        fp, fq, f0 = plain.trace.objective[:k], quad.trace.objective[:k], plain.trace.objective[0]
+        ok = (k >= 10 and np.array_equal(quad.trace.step_size[:k], plain.trace.step_size[:k])
+              and np.array_equal(quad.trace.objective_evals[:k], plain.trace.objective_evals[:k])
+              and bool(np.all(np.abs(fq - fp) <= 1e-9 * fp + 1e-14 * np.sqrt(fp * f0)))
+              and quad.status == plain.status and abs(quad.iters_ran - plain.iters_ran) <= 2)
+        if not ok:
+            fails.append(f"quadratic line search coh={coh}: rank {rank} {quad.status}/{plain.status} {quad.iters_ran}/{plain.iters_ran} k={k}")
+        obj.close()
     # the callers next to the hot path, sharded: solvesystem (src/engine/solve_system.jl) bit for bit,
     # the box log barrier (src/engine/primal_barrier.jl) at the libm tolerance
     n = 40_000

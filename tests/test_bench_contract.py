@@ -47,7 +47,9 @@ def test_ncu_traffic_lookup(bench):
     t, src = bench.ncu_traffic(_args(), 1, 200_000_000)
     assert t is not None and abs(t - 31.2e9) < 0.1e9 and "r1_ncu_full_ls_r1b.txt" in src
     assert bench.ncu_traffic(_args(), 2, 200_000_000) == (None, None)          # other configuration: no number
-    assert bench.ncu_traffic(_args(coh=0), 1, 200_000_000) == (None, None)
+    t0, src0 = bench.ncu_traffic(_args(coh=0), 1, 200_000_000)                # the banded-random headline: r2 capture
+    assert t0 is not None and abs(t0 - 30.5e9) < 0.3e9 and "k_spmv_direct" in src0
+    assert bench.ncu_traffic(_args(coh=5), 1, 200_000_000) == (None, None)
     assert bench.ncu_traffic(_args(workload="logreg"), 1, 20_000_000) == (None, None)
 
 
@@ -62,3 +64,21 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "iterations/s" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == pytest.approx(d["value"], rel=1e-4)
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a 1-thread row beside the all-core one, both on the same sample
+    cb = d["cpu_baseline"]
+    assert cb["rows"][0]["threads"] == cb["cores"] and cb["rows"][0]["iterations"] == 10
+    assert cb["single_thread"] is None or cb["single_thread"]["threads"] == 1
+    assert d["config"]["n"] == 400000 and "coh_log2=0" in d["config"]["workload"]
+
+
+def test_parity_fixture_lookup(bench, tmp_path, monkeypatch):
+    import numpy as np
+    monkeypatch.setattr(bench, "FIXTURE", str(tmp_path / "fx.json"))
+    a = _args(coh=0, quadratic_ls=False)
+    tr = np.array([3.0, 2.0, 1.0])
+    assert bench.parity_vs_n1(a, 1000, 0, tr)[0] is None                      # no fixture yet
+    bench.write_fixture(a, 1000, 0, tr)
+    assert bench.parity_vs_n1(a, 1000, 0, tr) == (0.0, "first 3 iterations")
+    rel, _ = bench.parity_vs_n1(a, 1000, 0, tr * (1 + 1e-12))
+    assert 0 < rel < 2e-12
+    assert bench.parity_vs_n1(a, 1000, 30, tr)[0] is None                     # another configuration
