@@ -46,6 +46,7 @@ _SIGS = {
     "cgo_ctx_set_reduction_ctas": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_set_gather_block_bytes": (C.c_int, [_vp, C.c_int64]),
     "cgo_ctx_set_sweep_window": (C.c_int, [_vp, C.c_int]),
+    "cgo_ctx_set_csr_mode": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_sm_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cgo_ctx_kernel_launches": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_timing": (C.c_int, [_vp, C.c_int]),

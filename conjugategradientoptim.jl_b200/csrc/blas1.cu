@@ -366,6 +366,38 @@ struct GradDots {
     }
 };
 
+// logistic loss and its derivative from the margins (csr.cu EpiLogit, oracle logreg_fdf), in place: z → c = −y σ;
+// Σ ℓ.  PUSH: this rank's shard of c also goes into every rank's all-gathered copy (peer memory), then flag
+// CGO_F_GPART + me of every rank
+template <bool PUSH>
+struct LogitLoss {
+    static constexpr int TCLASS = CGO_T_OTHER;
+    static constexpr int K = 1;
+    static constexpr int OCC = 2;
+    struct In { double2 z, y; };
+    double2 *zc;
+    const double2 *y;
+    void *const *dst_all;
+    int nranks;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const { return In{ld2rw(zc + q), cgo_ld2(y + q)}; }
+    __device__ __forceinline__ double one(double z, double yy, double (&acc)[K]) const {
+        const double t = -yy * z;
+        const double e = exp(-fabs(t));
+        const double l = (t > 0.0 ? t : 0.0) + log1p(e);
+        const double sg = t >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+        acc[0] = acc[0] + l;
+        return -yy * sg;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        double2 c;
+        c.x = one(in.z.x, in.y.x, acc);
+        c.y = v2 ? one(in.z.y, in.y.y, acc) : 0.0;
+        cgo_st2(zc + q, c);
+        if (PUSH) for (int r = 0; r < nranks; ++r) cgo_st2((double2 *)dst_all[r] + q, c);
+    }
+};
+
 // updateiteratesolvesys! (src/engine/solve_system.jl:237-253): x_next[i] = base[i] + m*df_xp[i]
 // (base = x_next itself as the reference writes it, or x for Alg. 3.1 as published)
 struct SolveSysProject {
@@ -942,6 +974,19 @@ int cgo_blas1_dots3(cgo_ctx *c, const double *a, const double *b, int64_t n, int
     Dots3 op;
     op.a = (const double2 *)a; op.b = (const double2 *)b;
     return launch_blas1(c, op, n, cgo_red_args(c, slot));
+}
+int cgo_blas1_logit(cgo_ctx *c, double *zc, const double *y, int64_t n, int slot, void *const *dst_all, unsigned long long epoch) {
+    RedArgs red = cgo_red_args(c, slot);
+    if (dst_all) {
+        LogitLoss<true> op;
+        op.zc = (double2 *)zc; op.y = (const double2 *)y; op.dst_all = dst_all; op.nranks = c->nranks;
+        red.flags_all = c->d_flags_peer; red.sig_all_slot = CGO_F_GPART; red.nranks = c->nranks; red.me = c->rank;
+        red.sig_val = epoch;
+        return launch_blas1(c, op, n, red);
+    }
+    LogitLoss<false> op;
+    op.zc = (double2 *)zc; op.y = (const double2 *)y; op.dst_all = nullptr; op.nranks = 1;
+    return launch_blas1(c, op, n, red);
 }
 int cgo_blas1_grad_dots(cgo_state *st) {
     GradDots op;

@@ -153,6 +153,12 @@ extern "C" int cgo_ctx_sm_count(cgo_ctx *c, int *sms) {
     *sms = c->sms;
     return 0;
 }
+extern "C" int cgo_ctx_set_csr_mode(cgo_ctx *c, int mode) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CHECK(mode >= 0 && mode <= 2, "cgo_ctx_set_csr_mode: mode %d out of [0,2]", mode);
+    c->csr_mode = mode;
+    return 0;
+}
 extern "C" int cgo_ctx_set_sweep_window(cgo_ctx *c, int tiles) {
     CGO_CHECK(c != nullptr, "NULL ctx");
     CGO_CHECK(tiles >= 0, "cgo_ctx_set_sweep_window: negative window");

@@ -480,27 +480,6 @@ struct EpiLogit {
     }
 };
 
-// Sample-sharded logistic regression over peer memory: row j of Aᵀ_r c_r belongs to the feature
-// shard of rank o; store it straight into rank o's receive block (slice `me`) — the all-to-all
-// fused into the SpMVᵀ epilogue.
-struct EpiPushPart {
-    static constexpr int K = 1, NOPS = 0;
-    static constexpr bool HAS_INIT = false;
-    struct Pre {};
-    __device__ __forceinline__ double init(const Pre &) const { return 0.0; }
-    void *const *recv_all;               // device table: rank o's g_recv + me * stride
-    const int64_t *flo;                  // device copy of the feature shard boundaries, nranks + 1
-    int nranks;
-    __device__ __forceinline__ const double *operand(int) const { return nullptr; }
-    __device__ __forceinline__ Pre load(const double *, int) const { return Pre(); }
-    __device__ __forceinline__ void row(int64_t j, double sum, const Pre &, double (&)[K]) const {
-        int o = (int)((j * nranks) / flo[nranks]);           // shards are near-uniform: a close first guess
-        while (o > 0 && j < flo[o]) --o;
-        while (o + 1 < nranks && j >= flo[o + 1]) ++o;
-        ((double *)recv_all[o])[j - flo[o]] = sum;
-    }
-};
-
 // Hessian-vector product of least squares, ∇²f u = Aᵀ(A u): v = A u with Σ v² (= u·Hu), then
 // hv = Aᵀ v with u·hv and hv·hv
 struct EpiStoreSq {
@@ -1257,6 +1236,18 @@ static int launch_csr_blocked(cgo_ctx *c, const CsrMat &A, const CsrBlocked &B, 
     return launch_csr_pass(c, B.blk[nb - 1], xg, with_init(epi, partial), red, tclass);
 }
 
+// the same with k_spmv_direct (sliced blocks): every pass just stores the running row sums, the epilogue and its
+// reductions are a BLAS-1 kernel of the caller's.  `wait`: flag hand-off that guards the gathered vector (first pass)
+static int spmv_direct_passes(cgo_ctx *c, const CsrMat &M, const CsrBlocked &B, const double *xg, double *out,
+                              const RedArgs *wait, int tclass) {
+    if (B.blk.empty()) return launch_direct(c, M, xg, DirStore{out}, dir_args(c, wait), tclass);
+    for (size_t j = 0; j < B.blk.size(); ++j) {
+        if (j == 0) CGO_TRY(launch_direct(c, B.blk[j], xg, DirStore{out}, dir_args(c, wait), tclass));
+        else CGO_TRY(launch_direct(c, B.blk[j], xg, DirStoreInit{out, out}, dir_args(c), tclass));
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ the objective
 struct CsrObj : cgo_obj {
     bool logreg = false;
@@ -1271,20 +1262,20 @@ struct CsrObj : cgo_obj {
     bool r_is_peer = false;
     double lambda = 0.0;
     int64_t nsamples = 0;
-    // sample-sharded logistic regression (nranks > 1): A holds this rank's samples × all features,
-    // AT its transpose; the state vectors are feature shards [flo[rank], flo[rank+1])
+    // sharded logistic regression (nranks > 1): samples AND features are sharded.  A holds this rank's samples ×
+    // all features and gathers the all-gathered trial point; AT holds this rank's FEATURES × all samples (built
+    // straight from the generator) and gathers the all-gathered c, so every row of Aᵀc is added over all samples in
+    // the single-GPU order.  The state vectors are feature shards [flo[rank], flo[rank+1]).
     bool lr_sharded = false;
-    std::vector<int64_t> flo;          // feature shard boundaries, nranks + 1
+    bool lr_direct = false;            // k_spmv_direct passes + BLAS-1 epilogues (sliced matrices)
+    std::vector<int64_t> flo, slo;     // feature / sample shard boundaries, nranks + 1
     double *xp_full = nullptr;         // all-gathered trial point, n_global
-    double *g_part = nullptr;          // Aᵀ_r c_r, n_global
-    double *g_recv = nullptr;          // nranks × part_stride: every rank's slice of my shard
-    int64_t part_stride = 0;
-    // peer-memory variant: xp_full and g_recv are mapped by every rank
+    double *c_full = nullptr;          // all-gathered c = −y σ, nsamples
+    // peer-memory variant: xp_full and c_full are mapped by every rank
     bool lr_peer = false;
-    std::vector<void *> xpf_peers, grecv_peers;
+    std::vector<void *> xpf_peers, cf_peers;
     void **d_xpf_dst = nullptr;        // rank r's xp_full + flo[me]
-    void **d_grecv_dst = nullptr;      // rank r's g_recv + me * part_stride
-    int64_t *d_flo = nullptr;
+    void **d_cf_dst = nullptr;         // rank r's c_full + slo[me]
     ~CsrObj() override {
         if (ctx && cgo_ctx_alive(ctx)) cudaSetDevice(ctx->device);
         csr_free(A); csr_free(AT);
@@ -1292,11 +1283,11 @@ struct CsrObj : cgo_obj {
         if (r_is_peer) { cgo_peer_free(ctx, r_base, rpeers, true); r_base = nullptr; }
         if (lr_peer) {
             cgo_peer_free(ctx, xp_full, xpf_peers, true); xp_full = nullptr;
-            cgo_peer_free(ctx, g_recv, grecv_peers, true); g_recv = nullptr;
+            cgo_peer_free(ctx, c_full, cf_peers, true); c_full = nullptr;
         }
-        cudaFree(d_xpf_dst); cudaFree(d_grecv_dst); cudaFree(d_flo);
+        cudaFree(d_xpf_dst); cudaFree(d_cf_dst);
         cudaFree(b); cudaFree(r_base); cudaFree(qv);
-        cudaFree(xp_full); cudaFree(g_part); cudaFree(g_recv);
+        cudaFree(xp_full); cudaFree(c_full);
     }
     int alloc_r() {
         size_t bytes = sizeof(double) * (size_t)(nrows + 2 * halo + 4);
@@ -1362,7 +1353,39 @@ struct CsrObj : cgo_obj {
     // ---- gather-bound matrices (sliced layout): k_spmv_direct + the dots as BLAS-1 passes
     bool direct() const { return A.sliced != 0; }
     void reduction_site(int32_t *V, int32_t *U) const override {
-        if (direct()) { *V = 2; *U = CGO_U_VEC; } else { *V = 1; *U = 1; }
+        if (direct() || lr_direct) { *V = 2; *U = CGO_U_VEC; } else { *V = 1; *U = 1; }
+    }
+    // logistic regression through k_spmv_direct.  One rank: K_a | passes of A → margins | logit + loss (BLAS-1) |
+    // passes of Aᵀ | /N + λw + dots (BLAS-1).  R ranks: K_a also stores its shard of xp into every rank's
+    // all-gathered copy; the logit kernel stores its shard of c into every rank's all-gathered c; flags hand the
+    // data to the consuming passes (without peer memory: two NCCL all-gathers).
+    int eval_trial_lr_direct(cgo_state *st, double a, bool fused, double beta, double *out) {
+        const int R = ctx->nranks;
+        const double invN = 1.0 / (double)nsamples;
+        RedArgs wx, wc;                           // flag waits of the first K_b / K_c pass
+        const RedArgs *pwx = nullptr, *pwc = nullptr;
+        unsigned long long e = 0;
+        if (R > 1 && lr_peer) {
+            e = ++ctx->epoch;
+            HaloPush hp;
+            hp.dst_all = d_xpf_dst; hp.epoch = e;
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                     // K_a + all-gather of xp
+            wx.wait_all = ctx->flags_local + CGO_F_XPALL; wx.wait_val = e; wx.nranks = R; pwx = &wx;
+            wc.wait_all = ctx->flags_local + CGO_F_GPART; wc.wait_val = e; wc.nranks = R; pwc = &wc;
+        } else {
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                          // K_a
+            if (R > 1) CGO_TRY(cgo_allgatherv_f64(ctx, st->xp, xp_full, flo.data()));
+        }
+        const double *w_all = R > 1 ? xp_full : st->xp;
+        CGO_TRY(spmv_direct_passes(ctx, A, Ab, w_all, r, pwx, CGO_T_SPMV));            // K_b: margins of my samples
+        CGO_TRY(cgo_blas1_logit(ctx, r, b, nrows, CGO_P_PHI, (R > 1 && lr_peer) ? d_cf_dst : nullptr, e));   // c, Σ loss [+ all-gather of c]
+        if (R > 1 && !lr_peer) CGO_TRY(cgo_allgatherv_f64(ctx, r, c_full, slo.data()));
+        const double *c_all = R > 1 ? c_full : r;
+        CGO_TRY(spmv_direct_passes(ctx, AT, ATb, c_all, st->gp, pwc, CGO_T_SPMVT));    // K_c: Aᵀc over my features
+        CGO_TRY(cgo_blas1_grad_combine(st, st->gp, 1, 0, invN, lambda));               // /N + λw, dots
+        CGO_TRY(cgo_finish_pack(ctx, 12, out));
+        out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
+        return 0;
     }
     int eval_trial_ls_direct(cgo_state *st, double a, bool fused, double beta, double *out) {
         const bool peer = r_is_peer && st->peer_x;
@@ -1457,44 +1480,8 @@ struct CsrObj : cgo_obj {
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
         if (!logreg && direct()) return eval_trial_ls_direct(st, a, fused, beta, out);
         if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);
-        if (lr_sharded && lr_peer) {
-            // the same data flow with both exchanges fused into the producing kernels: K_a stores
-            // its shard of xp into every rank's all-gathered copy, the last SpMVᵀ pass stores each
-            // row into its owner's receive block; flags hand the data to the consuming kernels
-            const unsigned long long e = ++ctx->epoch;
-            HaloPush hp;
-            hp.dst_all = d_xpf_dst; hp.epoch = e;
-            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                     // K_a + all-gather
-            EpiLogit e1{b, r};
-            RedArgs rb = cgo_red_args(ctx, CGO_P_PHI);
-            rb.wait_all = ctx->flags_local + CGO_F_XPALL; rb.wait_val = e; rb.nranks = ctx->nranks;
-            CGO_TRY(launch_csr_blocked(ctx, A, Ab, xp_full, e1, r, rb, CGO_T_SPMV, /*wait_first=*/true));   // K_b
-            EpiPushPart e2;
-            e2.recv_all = d_grecv_dst; e2.flo = d_flo; e2.nranks = ctx->nranks;
-            RedArgs rc = cgo_red_args(ctx, CGO_PACK_LEN - 1);
-            rc.flags_all = ctx->d_flags_peer; rc.sig_all_slot = CGO_F_GPART; rc.nranks = ctx->nranks; rc.me = ctx->rank;
-            rc.sig_val = e;
-            CGO_TRY(launch_csr_blocked(ctx, AT, ATb, r, e2, g_part, rc, CGO_T_SPMVT));             // K_c + all-to-all
-            CGO_TRY(cgo_blas1_grad_combine(st, g_recv, ctx->nranks, part_stride, 1.0 / (double)nsamples, lambda, e));
-            CGO_TRY(cgo_finish_pack(ctx, 12, out));
-            out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
-            return 0;
-        }
+        if (logreg && lr_direct) return eval_trial_lr_direct(st, a, fused, beta, out);
         CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                               // K_a
-        if (lr_sharded) {
-            // all-gather xp → margins of my samples → partial gradient over ALL features →
-            // all-to-all of shard slices → rank-ordered combine fused with the dot pack
-            CGO_TRY(cgo_allgatherv_f64(ctx, st->xp, xp_full, flo.data()));
-            EpiLogit e1{b, r};
-            CGO_TRY(launch_csr_blocked(ctx, A, Ab, xp_full, e1, r, cgo_red_args(ctx, CGO_P_PHI), CGO_T_SPMV));  // K_b
-            EpiStore e2{g_part};
-            CGO_TRY(launch_csr_blocked(ctx, AT, ATb, r, e2, g_part, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_SPMVT)); // K_c
-            CGO_TRY(cgo_alltoallv_f64(ctx, g_part, flo.data(), g_recv, part_stride));
-            CGO_TRY(cgo_blas1_grad_combine(st, g_recv, ctx->nranks, part_stride, 1.0 / (double)nsamples, lambda));
-            CGO_TRY(cgo_finish_pack(ctx, 12, out));
-            out[CGO_P_PHI] = out[CGO_P_PHI] / (double)nsamples + (0.5 * lambda) * out[CGO_P_XPXP];
-            return 0;
-        }
         CGO_TRY(exchange(st->xp, st->n));
         if (logreg) {
             EpiLogit e1{b, r};
@@ -1518,9 +1505,9 @@ struct CsrObj : cgo_obj {
     // A and Aᵀ streamed once (8 B value + 4 B index per entry + row pointers)
     // plus the vector passes R x,u W xp | gather xp, R b, W r | gather r, W g⁺, R u (,g)
     double bytes_per_eval() const override {
-        if (lr_sharded)     // K_a 24d_loc | A_r + gather + R y W c | Aᵀ_r + gather + W part (d) | combine R parts,u,g,w W g⁺
+        if (lr_direct)      // K_a 24d_loc | A_r + gather + W z | logit R z, y W c | Aᵀ_f + gather + W q | R q, u, g, w W g⁺
             return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
-                   8.0 * (3.0 * (double)nrows + 2.0 * (double)n_global + (8.0 + (double)ctx->nranks) * (double)n_local);
+                   8.0 * (5.0 * (double)nrows + (ctx->nranks > 1 ? (double)n_global + (double)nsamples : 0.0) + 11.0 * (double)n_local);
         // (gather-bound matrices: the dots are separate BLAS-1 passes, R r | R g⁺, g, u instead of the staged u, g)
         return 12.0 * (double)(A.nnz + AT.nnz) + 8.0 * (double)(A.nrows + 1 + AT.nrows + 1) +
                8.0 * (3.0 * (double)nrows + 6.0 * (double)n_local) + (direct() ? 8.0 * ((double)nrows + (double)n_local) : 0.0);
@@ -1544,27 +1531,23 @@ extern "C" int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n, int32
     CGO_CHECK(S == 0 || (W >= S && n > 2 * W), "sparse_ls: need W >= nnz_per_row-1 and n > 2W (n=%lld, W=%lld)", (long long)n, (long long)W);
     CGO_CHECK(coh_log2 >= 0 && coh_log2 < 31, "sparse_ls: coh_log2 out of range");
     CGO_CUDA(cudaSetDevice(ctx->device));
-    CsrObj *o = new CsrObj();
-    o->ctx = ctx; o->n_global = n;
-    int64_t lo, hi;
+    int64_t lo, hi, n_alloc = 0;
     CGO_TRY(cgo_shard_range(n, ctx->nranks, ctx->rank, 2, &lo, &hi));
-    o->offset = lo; o->n_local = hi - lo; o->nrows = hi - lo;
     for (int q = 0; q < ctx->nranks; ++q) {
         int64_t a, b;
         CGO_TRY(cgo_shard_range(n, ctx->nranks, q, 2, &a, &b));
-        if (b - a > o->n_alloc) o->n_alloc = b - a;
+        if (b - a > n_alloc) n_alloc = b - a;
     }
     const bool multi = ctx->nranks > 1;
-    o->halo = multi ? W : 0;
     if (multi) {
-        if (o->n_local < W || o->n_local + 2 * W > n) {
-            cgo_set_error("sparse_ls: shard of %lld rows needs W <= rows and rows + 2W <= n (W=%lld, n=%lld)",
-                          (long long)o->n_local, (long long)W, (long long)n);
-            delete o;
-            return 2;
-        }
+        CGO_CHECK(hi - lo >= W && hi - lo + 2 * W <= n, "sparse_ls: shard of %lld rows needs W <= rows and rows + 2W <= n (W=%lld, n=%lld)",
+                  (long long)(hi - lo), (long long)W, (long long)n);
         CGO_CHECK(W % 2 == 0, "sparse_ls: W must be even with more than one rank");
     }
+    CsrObj *o = new CsrObj();          // (nothing below returns without deleting it)
+    o->ctx = ctx; o->n_global = n;
+    o->offset = lo; o->n_local = hi - lo; o->nrows = hi - lo; o->n_alloc = n_alloc;
+    o->halo = multi ? W : 0;
     LsSpec sp;
     sp.n = n; sp.K = K; sp.coh = coh_log2; sp.W = W; sp.w = S > 0 ? (2 * W) / S : 0; sp.seed = seed;
     const int64_t nloc = o->n_local, nnz = nloc * K;
@@ -1652,78 +1635,121 @@ extern "C" int cgo_obj_sparse_ls_create_csr(cgo_ctx *ctx, int64_t nrows, int64_t
     return 0;
 }
 
+// rows [flo, fhi) of Aᵀ over ALL samples, straight from the generator (sharded logistic regression): feature c
+// lies in stratum c / w, so only the entries k of the strata that overlap the shard have to be looked at
+struct LrFeatSrc {
+    LrSpec s;
+    int64_t flo, fhi, total;        // total = N * nk candidates
+    int32_t k0, nk;
+    __device__ __forceinline__ bool get(int64_t e, int64_t &trow, int64_t &key) const {
+        const int64_t i = e / nk;
+        const int k = k0 + (int)(e - i * nk);
+        int64_t c; double v;
+        s.entry(i, k, c, v);
+        if (c < flo || c >= fhi) return false;
+        trow = c - flo; key = i * s.K + k;
+        return true;
+    }
+};
+struct LrFeatFin {                  // key = global entry index of the generator; column = global sample index
+    LrSpec s;
+    __device__ __forceinline__ void get(int64_t key, int32_t &srow, double &v) const {
+        const int64_t i = key / s.K;
+        int64_t c;
+        s.entry(i, (int)(key - i * s.K), c, v);
+        srow = (int32_t)i;
+    }
+};
+
 extern "C" int cgo_obj_logreg_create_synthetic(cgo_ctx *ctx, int64_t N, int64_t d, int32_t K, uint64_t seed,
                                                double lambda, cgo_obj **out) {
     CGO_CHECK(ctx && out, "NULL argument");
     CGO_CHECK(K >= 1 && N >= 1 && d >= K, "logreg: need nnz_per_row >= 1, nsamples >= 1, nfeat >= nnz_per_row");
-    const int R = ctx->nranks;
+    const int R = ctx->nranks, me = ctx->rank;
     CGO_CHECK(R == 1 || (N >= 2 * R && d >= 2 * R), "logreg: %d ranks need nsamples >= %d and nfeat >= %d", R, 2 * R, 2 * R);
+    CGO_CHECK(R == 1 || ctx->csr_mode != 1, "logreg: the sharded objective runs on k_spmv_direct (CGO_CSR_MODE=1 forbids it)");
     CGO_CUDA(cudaSetDevice(ctx->device));
     CsrObj *o = new CsrObj();
     o->ctx = ctx; o->logreg = true; o->lambda = lambda; o->nsamples = N;
     o->n_global = d; o->halo = 0;
-    // samples (rows of A) and features (state vectors) are both sharded contiguously
-    int64_t slo = 0, shi = N;
-    o->flo.assign(R + 1, 0);
-    for (int r = 0; r < R; ++r) {
-        int64_t lo, hi;
-        CGO_TRY(cgo_shard_range(d, R, r, 2, &lo, &hi));
-        o->flo[r] = lo; o->flo[r + 1] = hi;
-        if (hi - lo > o->part_stride) o->part_stride = hi - lo;
-    }
-    o->part_stride = (o->part_stride + 3) & ~(int64_t)1;          // even, with one element of slack
-    CGO_TRY(cgo_shard_range(N, R, ctx->rank, 2, &slo, &shi));
-    o->offset = o->flo[ctx->rank]; o->n_local = o->flo[ctx->rank + 1] - o->flo[ctx->rank];
-    o->nrows = shi - slo;
-    o->lr_sharded = R > 1;
     LrSpec sp;
     sp.N = N; sp.d = d; sp.K = K; sp.w = d / K; sp.seed = seed;
-    const int64_t nloc = o->nrows;
     auto body = [&]() -> int {
-        CGO_TRY(check_i32(nloc > d ? nloc : d, "matrix dimension"));
+        // samples (rows of A) and features (state vectors, rows of Aᵀ) are both sharded contiguously
+        o->flo.assign(R + 1, 0); o->slo.assign(R + 1, 0);
+        for (int r = 0; r < R; ++r) {
+            int64_t lo, hi;
+            CGO_TRY(cgo_shard_range(d, R, r, 2, &lo, &hi));
+            o->flo[r] = lo; o->flo[r + 1] = hi;
+            CGO_TRY(cgo_shard_range(N, R, r, 2, &lo, &hi));
+            o->slo[r] = lo; o->slo[r + 1] = hi;
+        }
+        const int64_t slo = o->slo[me], nloc = o->slo[me + 1] - o->slo[me];
+        o->offset = o->flo[me]; o->n_local = o->flo[me + 1] - o->flo[me];
+        o->nrows = nloc;
+        o->lr_sharded = R > 1;
+        CGO_TRY(check_i32(N > d ? N : d, "matrix dimension"));
         CGO_TRY(csr_alloc(o->A, nloc, nloc * K));
         CGO_CUDA(cudaMalloc(&o->b, sizeof(double) * (size_t)(nloc + CSR_PAD)));
+        CGO_CUDA(cudaMemsetAsync(o->b, 0, sizeof(double) * (size_t)(nloc + CSR_PAD), ctx->stream));
         k_lr_fill_A<<<grid_for(nloc, ctx->sms), 256, 0, ctx->stream>>>(sp, slo, nloc, o->A, o->b);
         CGO_CUDA(cudaGetLastError());
         CGO_TRY(o->alloc_r());
-        CsrSrc src{o->A.col, nloc * K};
-        FixedKFin fin{K, o->A.val};
-        CGO_TRY(build_transpose(ctx, src, fin, d, o->AT));
-        // K_b gathers over all d features, K_c over this rank's samples
+        if (R == 1) {
+            CsrSrc src{o->A.col, nloc * K};
+            FixedKFin fin{K, o->A.val};
+            CGO_TRY(build_transpose(ctx, src, fin, d, o->AT));
+        } else {
+            const int64_t flo = o->flo[me], fhi = o->flo[me + 1];
+            int64_t k0 = flo / sp.w, k1 = (fhi - 1) / sp.w;
+            if (k0 > K - 1) k0 = K - 1;
+            if (k1 > K - 1) k1 = K - 1;
+            LrFeatSrc src{sp, flo, fhi, N * (k1 - k0 + 1), (int32_t)k0, (int32_t)(k1 - k0 + 1)};
+            LrFeatFin fin{sp};
+            CGO_TRY(build_transpose(ctx, src, fin, fhi - flo, o->AT));
+        }
+        // K_b gathers over all d features, K_c over all N samples
         CGO_TRY(build_blocked(ctx, o->A, d, o->Ab));
-        CGO_TRY(build_blocked(ctx, o->AT, nloc, o->ATb));
-        if ((!o->Ab.blk.empty() || !o->ATb.blk.empty()) && o->A.nnz > (int64_t)200000000) {
+        CGO_TRY(build_blocked(ctx, o->AT, N, o->ATb));
+        const bool blocked = !o->Ab.blk.empty() || !o->ATb.blk.empty();
+        if (blocked && o->A.nnz > (int64_t)200000000 / R) {
             // production sizes: drop the single-pass copies (only the CSR test hooks read them)
             if (!o->Ab.blk.empty()) { cudaFree(o->A.col); cudaFree(o->A.val); o->A.col = nullptr; o->A.val = nullptr; }
             if (!o->ATb.blk.empty()) { cudaFree(o->AT.col); cudaFree(o->AT.val); o->AT.col = nullptr; o->AT.val = nullptr; }
             o->have_unblocked = false;
         }
+        // uniformly random columns: gather-bound (k_spmv_direct + BLAS-1 epilogues) whenever the gathers are what
+        // costs — column-blocked sizes, and always when sharded
+        o->lr_direct = ctx->csr_mode != 1 && (R > 1 || blocked || ctx->csr_mode == 2);
+        if (o->lr_direct) {
+            if (o->Ab.blk.empty()) CGO_TRY(csr_make_sliced(ctx, o->A));
+            if (o->ATb.blk.empty()) CGO_TRY(csr_make_sliced(ctx, o->AT));
+            for (auto &m : o->Ab.blk) CGO_TRY(csr_make_sliced(ctx, m));
+            for (auto &m : o->ATb.blk) CGO_TRY(csr_make_sliced(ctx, m));
+        }
         if (o->lr_sharded) {
-            const size_t xb = sizeof(double) * (size_t)(d + CSR_PAD), gb = sizeof(double) * (size_t)(o->part_stride * R + CSR_PAD);
-            CGO_CUDA(cudaMalloc(&o->g_part, xb));
+            const size_t xb = sizeof(double) * (size_t)(d + CSR_PAD), cb = sizeof(double) * (size_t)(N + CSR_PAD);
             if (ctx->peer_ok) {
                 void *p = nullptr;
                 o->lr_peer = true;
                 CGO_TRY(cgo_peer_alloc(ctx, xb, &p, o->xpf_peers));
                 o->xp_full = (double *)p;
-                CGO_TRY(cgo_peer_alloc(ctx, gb, &p, o->grecv_peers));
-                o->g_recv = (double *)p;
-                std::vector<void *> xd((size_t)R), gd((size_t)R);
+                CGO_TRY(cgo_peer_alloc(ctx, cb, &p, o->cf_peers));
+                o->c_full = (double *)p;
+                std::vector<void *> xd((size_t)R), cd((size_t)R);
                 for (int r = 0; r < R; ++r) {
-                    xd[(size_t)r] = (double *)o->xpf_peers[(size_t)r] + o->flo[(size_t)ctx->rank];
-                    gd[(size_t)r] = (double *)o->grecv_peers[(size_t)r] + (size_t)ctx->rank * o->part_stride;
+                    xd[(size_t)r] = (double *)o->xpf_peers[(size_t)r] + o->flo[(size_t)me];
+                    cd[(size_t)r] = (double *)o->cf_peers[(size_t)r] + o->slo[(size_t)me];
                 }
                 CGO_CUDA(cudaMalloc(&o->d_xpf_dst, sizeof(void *) * (size_t)R));
-                CGO_CUDA(cudaMalloc(&o->d_grecv_dst, sizeof(void *) * (size_t)R));
-                CGO_CUDA(cudaMalloc(&o->d_flo, sizeof(int64_t) * (size_t)(R + 1)));
+                CGO_CUDA(cudaMalloc(&o->d_cf_dst, sizeof(void *) * (size_t)R));
                 CGO_CUDA(cudaMemcpy(o->d_xpf_dst, xd.data(), sizeof(void *) * (size_t)R, cudaMemcpyHostToDevice));
-                CGO_CUDA(cudaMemcpy(o->d_grecv_dst, gd.data(), sizeof(void *) * (size_t)R, cudaMemcpyHostToDevice));
-                CGO_CUDA(cudaMemcpy(o->d_flo, o->flo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice));
+                CGO_CUDA(cudaMemcpy(o->d_cf_dst, cd.data(), sizeof(void *) * (size_t)R, cudaMemcpyHostToDevice));
             } else {
                 CGO_CUDA(cudaMalloc(&o->xp_full, xb));
-                CGO_CUDA(cudaMalloc(&o->g_recv, gb));
+                CGO_CUDA(cudaMalloc(&o->c_full, cb));
                 CGO_CUDA(cudaMemsetAsync(o->xp_full, 0, xb, ctx->stream));
-                CGO_CUDA(cudaMemsetAsync(o->g_recv, 0, gb, ctx->stream));
+                CGO_CUDA(cudaMemsetAsync(o->c_full, 0, cb, ctx->stream));
             }
             CGO_CUDA(cudaStreamSynchronize(ctx->stream));
         }

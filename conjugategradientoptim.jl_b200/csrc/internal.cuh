@@ -218,6 +218,8 @@ int cgo_blas1_axpy_dir(cgo_state *st, double a, bool fused_dir, double beta, con
 int cgo_blas1_residual_axpy(cgo_ctx *ctx, double *r, const double *v, double a, int64_t nrows, int slot);
 int cgo_blas1_sumsq(cgo_ctx *ctx, const double *a, int64_t n, int slot);                        // Σ a²
 int cgo_blas1_dots3(cgo_ctx *ctx, const double *a, const double *b, int64_t n, int slot);       // {a·b, b·b, a·a}
+// margins → c = −y σ in place, Σ loss → pack slot; dst_all != NULL: also all-gather c over peer memory (flag CGO_F_GPART)
+int cgo_blas1_logit(cgo_ctx *ctx, double *zc, const double *y, int64_t n, int slot, void *const *dst_all, unsigned long long epoch);
 int cgo_blas1_grad_dots(cgo_state *st);     // the eight dots of EpiGrad over (g⁺, g, u) → pack slots CGO_P_DPHI…
 // sample-sharded logistic regression: g⁺ = (Σ_r q[r·stride + i]) / N + λ xp, partial gradients
 // added in rank order, fused with the dot pack of EpiGrad (slots CGO_P_DPHI .. CGO_P_UU)

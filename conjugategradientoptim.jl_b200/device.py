@@ -41,6 +41,10 @@ class Context:
         """Column-block size for objectives with large random gathers (0 disables blocking)."""
         check(lib().cgo_ctx_set_gather_block_bytes(self.h, int(nbytes)))
 
+    def set_csr_mode(self, mode: int):
+        """SpMV kernel family of CSR objectives created afterwards: 0 per matrix, 1 fused k_csr_rows, 2 k_spmv_direct."""
+        check(lib().cgo_ctx_set_csr_mode(self.h, int(mode)))
+
     def set_sweep_window(self, tiles: int):
         """Lockstep window of the CSR sweep in tiles per CTA (0: free-running); results do not depend on it."""
         check(lib().cgo_ctx_set_sweep_window(self.h, int(tiles)))

@@ -96,6 +96,11 @@ int cgo_ctx_set_gather_block_bytes(cgo_ctx *ctx, int64_t bytes);
  * own 256-row tiles ahead of the grid's average progress, so that all CTAs gather from the same L2-resident
  * band of the vector (default 8; 0 = free-running; environment CGO_SWEEP_WINDOW).  Results do not depend on it. */
 int cgo_ctx_set_sweep_window(cgo_ctx *ctx, int tiles);
+/* which SpMV kernel family CSR objectives created afterwards use: 0 = per matrix (default: k_spmv_direct + BLAS-1
+ * dots when its gathers do not coalesce, the fused k_csr_rows otherwise), 1 = always k_csr_rows, 2 = always
+ * k_spmv_direct (environment CGO_CSR_MODE).  Changes the canonical order of the dots (cgo_obj_reduction_site),
+ * not the row sums. */
+int cgo_ctx_set_csr_mode(cgo_ctx *ctx, int mode);
 int cgo_ctx_sm_count(cgo_ctx *ctx, int *sms);
 int cgo_ctx_kernel_launches(cgo_ctx *ctx, int64_t *count);  /* kernels launched so far */
 /* optional per-launch CUDA-event timing on the ctx stream, by kernel class:

@@ -358,7 +358,8 @@ static double logreg_fdf(orc_objective *o, double *g, const double *w) {
         double sg = t >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
         c[i] = -y * sg;
     }
-    double loss = (o->sum_mode == ORC_SUM_CGO ? orc_sum_cgo(lp, N, 1, 2)
+    /* row-per-lane epilogue (V=1, U=1), or the BLAS-1 logit kernel of the k_spmv_direct path (V=2, U=4) */
+    double loss = (o->sum_mode == ORC_SUM_CGO ? (o->trial_V == 2 ? cgo_reduce(sum_term, lp, N, 2, g_blas1_U, 2) : orc_sum_cgo(lp, N, 1, 2))
                                               : orc_sum(lp, N, o->sum_mode, o->threads)) / (double)N;
     free(lp);
     csr_mv(o->n, o->rowptrT, o->colT, o->valT, c, g, o->threads);

@@ -137,7 +137,9 @@ def main():
         lo, hi = obj.offset, obj.offset + obj.n_local
         assert (lo, hi) == cg.shard_range(d, world, rank, 2) and obj.n_global == d
         ret = cg.minimizeobjective(obj, np.zeros(hi - lo), cfg, ls)
-        ora = O.minimize(O.Objective.logreg(N, d, 20, 24, lam), np.zeros(d), ocfg)
+        ora_obj = O.Objective.logreg(N, d, 20, 24, lam)
+        ora_obj.set_trial_site(*obj.trial_site)
+        ora = O.minimize(ora_obj, np.zeros(d), ocfg)
         k = min(50, len(ora.trace_objective), len(ret.trace.objective))
         ok = (k >= 10 and ret.status == ora.status and abs(ret.iters_ran - ora.iters_ran) <= 2
               and np.array_equal(ret.trace.step_size[:k], ora.trace_step_size[:k])

@@ -41,6 +41,7 @@ def test_f_and_g_match_oracle(ctx, N, d, K):
     lam = 1e-4
     obj = cg.LogRegGPU(N, d, K, 24, lam, ctx)
     ora = O.Objective.logreg(N, d, K, 24, lam)
+    ora.set_trial_site(*obj.trial_site)
     ora.set_sum_mode("cgo")
     rng = np.random.default_rng(1)
     for scale in (0.0, 0.1, 3.0, 40.0):                             # incl. saturated sigmoids
@@ -105,17 +106,24 @@ def test_column_blocked_passes_are_bit_identical(block_elems):
     """Large random gathers are evaluated one L2-sized column block per pass (csr.cu CsrBlocked);
     passes chain the row sums, so f, g and whole runs must not change by a single bit."""
     N, d, lam = 20_000, 3000, 1e-4
-    c0, c1 = cg.Context(0), cg.Context(0)
+    c0, c1, c2 = cg.Context(0), cg.Context(0), cg.Context(0)
     c0.set_gather_block_bytes(0)
+    c0.set_csr_mode(2)                       # single pass through k_spmv_direct: same kernels, same order of the dots
     c1.set_gather_block_bytes(8 * block_elems)
+    c2.set_gather_block_bytes(0)             # single pass through the fused k_csr_rows (dots in the row-per-lane order)
     a, b = cg.LogRegGPU(N, d, 20, 24, lam, c0), cg.LogRegGPU(N, d, 20, 24, lam, c1)
+    f = cg.LogRegGPU(N, d, 20, 24, lam, c2)
     assert a.csr_blocks(False) == 1 and a.csr_blocks(True) == 1
     assert b.csr_blocks(False) == -(-d // block_elems) and b.csr_blocks(True) == -(-N // block_elems)
+    assert a.trial_site == b.trial_site == (2, 4) and f.trial_site == (1, 1)
     w = 0.5 * np.random.default_rng(3).standard_normal(d)
     wa, wb = a.make_workspace(w, fuse_direction=False), b.make_workspace(w, fuse_direction=False)
+    wf = f.make_workspace(w, fuse_direction=False)
     assert wa.f_x0 == wb.f_x0 and np.array_equal(wa.pack, wb.pack)
     assert np.array_equal(wa.download()[1], wb.download()[1])
-    wa.close(); wb.close()
+    assert np.array_equal(wa.download()[1], wf.download()[1])          # the gradient does not depend on the kernel family
+    assert abs(wf.f_x0 - wa.f_x0) <= 1e-14 * abs(wa.f_x0)              # the loss only through the order of its sum
+    wa.close(); wb.close(); wf.close(); f.close(); c2.close()
     _, cfg, ls = make_pair("LBFGS", max_iters=25, c1=1e-4, c2=0.9)
     ra = cg.minimizeobjective(a, np.zeros(d), cfg, ls)
     rb = cg.minimizeobjective(b, np.zeros(d), cfg, ls)
