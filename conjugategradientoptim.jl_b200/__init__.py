@@ -20,7 +20,7 @@ from .engine import (BoxConstraint, CvxInequalityConstraint, LinesearchSolveSys,
                      minimizeobjectivererun, primalbarriermethod_, setupCvxInequalityConstraint,
                      setupLinesearchSolveSys, setupPrimalBarrierConfig, solvesystem, verifyt0)
 from .engine.optim import linesearch_  # noqa: F401
-from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceVector,  # noqa: F401
+from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceStart, DeviceVector,  # noqa: F401
                      BoxBarrierGPU, LogRegGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,
                      dot, shard_range, BatchedResults, minimizeobjective_batched, batched_lanes)
 from .device import DeviceLineSearchContainer as LineSearchContainer  # noqa: F401

@@ -75,6 +75,7 @@ _SIGS = {
     "cgo_obj_csr_download": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
     "cgo_obj_spmv": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "cgo_state_create": (C.c_int, [_vp, _vp, _dp, C.c_int32, C.POINTER(_vp), _dp]),
+    "cgo_state_create_from_state": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp), _dp]),
     "cgo_state_destroy": (C.c_int, [_vp]),
     "cgo_reset_direction": (C.c_int, [_vp, _dp]),
     "cgo_eval_trial": (C.c_int, [_vp, C.c_double, _dp]),

@@ -79,6 +79,10 @@ class Results:
     iters_ran: int
     status: str
     trace: TraceContainer
+    # not in the reference: host → device bytes the run's start cost (0 for a DeviceStart), and — on request
+    # (keep_workspace) — the run's live device state, from which a restart can begin without a host round trip
+    h2d_bytes: int = 0
+    workspace: Any = None
 
 
 def updateresult_(ret: Results, x, df_x, f_x, i: int, status: str) -> None:

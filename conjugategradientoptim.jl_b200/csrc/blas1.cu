@@ -829,56 +829,71 @@ extern "C" int cgo_state_destroy(cgo_state *st) {
     return 0;
 }
 
-extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, int32_t lbfgs_m,
-                                cgo_state **out_state, double out[CGO_PACK_LEN]) {
+// x0: host pointer (x0_on_device = false: one H2D) or device pointer (one D2D)
+static int state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, bool x0_on_device, int32_t lbfgs_m,
+                        cgo_state **out_state, double out[CGO_PACK_LEN]) {
     CGO_CHECK(ctx && obj && x0 && out_state && out, "cgo_state_create: NULL argument");
     CGO_CHECK(obj->ctx == ctx, "objective belongs to another ctx");
     CGO_CHECK(lbfgs_m >= 0 && lbfgs_m <= CGO_LBFGS_MAX_M, "lbfgs_m=%d out of [0,%d]", lbfgs_m, CGO_LBFGS_MAX_M);
+    CGO_CHECK(obj->halo % 2 == 0, "halo must be even");      // keeps the local part 16-byte aligned
     CGO_CUDA(cudaSetDevice(ctx->device));
     cgo_state *st = new cgo_state();
     st->ctx = ctx; st->obj = obj; st->n = obj->n_local; st->halo = obj->halo;
-    // halo must keep 16-byte alignment of the local part
-    CGO_CHECK(st->halo % 2 == 0, "halo must be even");
-    double **ptrs[5] = {&st->x, &st->g, &st->u, &st->xp, &st->gp};
-    st->peer_x = ctx->nranks > 1 && ctx->peer_ok && st->halo > 0;
-    for (int i = 0; i < 5; ++i) {
-        int r;
-        if (st->peer_x && (i == 0 || i == 3)) {      // x and xp: mapped by the ring neighbours
-            void *p = nullptr;
-            // same size on every rank: the ranks pool and reuse these blocks in lockstep
-            const int64_t len = (obj->n_alloc > st->n ? obj->n_alloc : st->n) + 2 * st->halo + 4;
-            r = cgo_peer_alloc(ctx, sizeof(double) * (size_t)len, &p, st->xpeers[i == 0 ? 0 : 1]);
-            st->base[i] = (double *)p;
-            *ptrs[i] = st->base[i] + st->halo;
-        } else {
-            r = alloc_vec(st, &st->base[i], ptrs[i]);
+    auto body = [&]() -> int {                     // (every failure below goes through cgo_state_destroy)
+        double **ptrs[5] = {&st->x, &st->g, &st->u, &st->xp, &st->gp};
+        st->peer_x = ctx->nranks > 1 && ctx->peer_ok && st->halo > 0;
+        for (int i = 0; i < 5; ++i) {
+            if (st->peer_x && (i == 0 || i == 3)) {      // x and xp: mapped by the ring neighbours
+                void *p = nullptr;
+                // same size on every rank: the ranks pool and reuse these blocks in lockstep
+                const int64_t len = (obj->n_alloc > st->n ? obj->n_alloc : st->n) + 2 * st->halo + 4;
+                CGO_TRY(cgo_peer_alloc(ctx, sizeof(double) * (size_t)len, &p, st->xpeers[i == 0 ? 0 : 1]));
+                st->base[i] = (double *)p;
+                *ptrs[i] = st->base[i] + st->halo;
+            } else {
+                CGO_TRY(alloc_vec(st, &st->base[i], ptrs[i]));
+            }
         }
-        if (r) { cgo_state_destroy(st); return r; }
-    }
-    st->xp_alloc = 1;
-    st->m = lbfgs_m;
-    if (lbfgs_m > 0) {
-        const size_t hist_bytes = sizeof(double) * (size_t)(st->n + 4);
-        for (int k = 0; k < lbfgs_m; ++k) {
-            void *s = nullptr, *y = nullptr;
-            CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &s));
-            st->S.push_back((double *)s);
-            CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &y));
-            st->Y.push_back((double *)y);
+        st->xp_alloc = 1;
+        st->m = lbfgs_m;
+        if (lbfgs_m > 0) {
+            const size_t hist_bytes = sizeof(double) * (size_t)(st->n + 4);
+            for (int k = 0; k < lbfgs_m; ++k) {
+                void *s = nullptr, *y = nullptr;
+                CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &s));
+                st->S.push_back((double *)s);
+                CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &y));
+                st->Y.push_back((double *)y);
+            }
+            st->rho.assign(lbfgs_m, 0.0);
+            void *q = nullptr;
+            CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &q));
+            st->q = (double *)q;
         }
-        st->rho.assign(lbfgs_m, 0.0);
-        void *q = nullptr;
-        CGO_TRY(cgo_dev_alloc(ctx, hist_bytes, &q));
-        st->q = (double *)q;
-    }
-    // optim.jl:21 x = copy(x_initial); :25 f_x = fdf!(df_x, x): evaluate at x0 through the trial
-    // kernels with u = 0, a = 0 (xp = x0 + 0*0 = x0 exactly), then adopt (xp, g⁺) as (x, g).
-    CGO_CUDA(cudaMemcpyAsync(st->x, x0, sizeof(double) * (size_t)st->n, cudaMemcpyHostToDevice, ctx->stream));
-    int r = obj->eval_trial(st, 0.0, false, 0.0, out);
-    if (r) { cgo_state_destroy(st); return r; }
+        // optim.jl:21 x = copy(x_initial); :25 f_x = fdf!(df_x, x): evaluate at x0 through the trial
+        // kernels with u = 0, a = 0 (xp = x0 + 0*0 = x0 exactly), then adopt (xp, g⁺) as (x, g).
+        CGO_CUDA(cudaMemcpyAsync(st->x, x0, sizeof(double) * (size_t)st->n,
+                                 x0_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        CGO_TRY(obj->eval_trial(st, 0.0, false, 0.0, out));
+        return 0;
+    };
+    const int rc = body();
+    if (rc) { cgo_state_destroy(st); return rc; }
     cgo_accept(st);
     *out_state = st;
     return 0;
+}
+extern "C" int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0, int32_t lbfgs_m,
+                                cgo_state **out_state, double out[CGO_PACK_LEN]) {
+    return state_create(ctx, obj, x0, false, lbfgs_m, out_state, out);
+}
+extern "C" int cgo_state_create_from_state(cgo_ctx *ctx, cgo_obj *obj, cgo_state *src, int32_t which, int32_t lbfgs_m,
+                                           cgo_state **out_state, double out[CGO_PACK_LEN]) {
+    CGO_CHECK(src != nullptr, "cgo_state_create_from_state: NULL source state");
+    CGO_CHECK(src->ctx == ctx && src->n == (obj ? obj->n_local : -1), "source state belongs to another ctx or has another dimension");
+    double *v[5] = {src->x, src->g, src->u, src->xp, src->gp};
+    CGO_CHECK(which >= 0 && which < 5, "which=%d out of range", which);
+    return state_create(ctx, obj, v[which], true, lbfgs_m, out_state, out);
 }
 
 extern "C" int cgo_accept(cgo_state *st) {

@@ -300,6 +300,15 @@ def dot(a: DeviceVector, b: DeviceVector):
     raise NotImplementedError(f"dot({a.name}, {b.name}) is not on the hot path")
 
 
+class DeviceStart:
+    """`x_initial` that already lives on the device: the iterate `x` of a live workspace.  minimizeobjective copies
+    it device to device (cgo_state_create_from_state) instead of uploading a host vector."""
+    __slots__ = ("ws",)
+
+    def __init__(self, ws):
+        self.ws = ws
+
+
 class DeviceLineSearchContainer:
     """LineSearchContainer (types.jl:84-100) + x, df_x of optim.jl:20-21, resident in HBM.
 
@@ -317,16 +326,24 @@ class DeviceLineSearchContainer:
         self._q_a = None                      # last trial step, not yet materialised
         if self.quadratic:
             fuse_direction = False            # there is no trial kernel for the direction update to ride on
-        x0 = np.ascontiguousarray(x_initial, dtype=np.float64)
-        if x0.shape != (objective.n_local,):
-            raise ValueError(f"x_initial has shape {x0.shape}, objective shard has n={objective.n_local}")
         self.objective = objective
         self.n = objective.n_local
         self.fuse_direction = fuse_direction
         self.beta_form = beta_form
         self._buf = np.zeros(PACK_LEN)
         self.h = C.c_void_p()
-        check(lib().cgo_state_create(objective.ctx.h, objective.h, dptr(x0), lbfgs_m, C.byref(self.h), dptr(self._buf)))
+        self.h2d_bytes = 0                    # host → device bytes this workspace cost (x_initial)
+        if isinstance(x_initial, DeviceStart):
+            src = x_initial.ws
+            if src.h is None or not src.h or src.n != self.n:
+                raise ValueError("DeviceStart: the source workspace is closed or has another dimension")
+            check(lib().cgo_state_create_from_state(objective.ctx.h, objective.h, src.h, 0, lbfgs_m, C.byref(self.h), dptr(self._buf)))
+        else:
+            x0 = np.ascontiguousarray(x_initial, dtype=np.float64)
+            if x0.shape != (objective.n_local,):
+                raise ValueError(f"x_initial has shape {x0.shape}, objective shard has n={objective.n_local}")
+            check(lib().cgo_state_create(objective.ctx.h, objective.h, dptr(x0), lbfgs_m, C.byref(self.h), dptr(self._buf)))
+            self.h2d_bytes = 8 * self.n
         self.f_x0 = f64(self._buf[P_PHI])
         self.norm_df_x0 = np.sqrt(f64(self._buf[P_GPGP]))
         self.pack = self._buf.copy()          # last trial pack

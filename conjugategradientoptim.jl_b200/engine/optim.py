@@ -146,7 +146,7 @@ class MinimizerRun:
 
 def minimizeobjective(fdf_, x_initial, config: CGConfig, linesearch_config: LineSearchConfig, *,
                       fuse_direction: bool = True, beta_form: str = "fused",
-                      quadratic_linesearch: bool = False) -> Results:
+                      quadratic_linesearch: bool = False, keep_workspace: bool = False) -> Results:
     """minimizeobjective (src/engine/optim.jl:6-171).
 
     `fdf_` is a device objective handle; `x_initial` a host vector (this rank's shard); the
@@ -157,25 +157,54 @@ def minimizeobjective(fdf_, x_initial, config: CGConfig, linesearch_config: Line
     equal pack form; `quadratic_linesearch` (CSR least squares) evaluates the trials
     of each line search from v = A u — one SpMV and one SpMVᵀ per iteration whatever the number of
     trials; ϕ then comes from ½r·r + a r·v + ½a² v·v, so decisions agree with the plain path up to
-    rounding.
+    rounding.  `x_initial` may be a `DeviceStart` (the iterate of a live workspace: no upload); `keep_workspace`
+    leaves the run's device state alive in `ret.workspace` (caller closes it) so that a restart can begin from it.
     """
     run = MinimizerRun(fdf_, x_initial, config, linesearch_config, fuse_direction, beta_form,
                        quadratic_linesearch)
     run.run()
     ret = run.results()
-    run.info.close()
+    ret.h2d_bytes = getattr(run.info, "h2d_bytes", 0)
+    if keep_workspace:
+        ret.workspace = run.info
+    else:
+        run.info.close()
     return ret
 
 
 def minimizeobjectivererun(fdf_, x_initial, config: CGConfig, linesearch_config: LineSearchConfig,
                            *rerun_config_tuples: Tuple[CGConfig, LineSearchConfig], **kw) -> List[Results]:
     """minimizeobjectivererun (src/engine/optim.jl:173-208)."""
-    rets = [minimizeobjective(fdf_, x_initial, config, linesearch_config, **kw)]      # :183-188
-    for rerun_config, backup_linesearch_config in rerun_config_tuples:                # :191
-        if rets[-1].status != "success":
-            ret = minimizeobjective(fdf_, rets[-1].minimizer, rerun_config,           # :195-200
-                                    backup_linesearch_config, **kw)
-            rets.append(ret)
-        else:
-            return rets                                                               # :203
+    # the next attempt starts from rets[end].minimizer (:197): that vector is still on the device, in the previous
+    # attempt's workspace — start from it there (DeviceStart: one D2D copy) instead of uploading the host copy
+    from ..device import DeviceStart
+    keep = kw.pop("keep_workspace", False)
+    live = []
+
+    def attempt(x0, cfg, ls):
+        ret = minimizeobjective(fdf_, x0, cfg, ls, keep_workspace=True, **kw)
+        live.append(ret.workspace)
+        for ws in live[:-1]:
+            ws.close()
+        del live[:-1]
+        return ret
+
+    try:
+        rets = [attempt(x_initial, config, linesearch_config)]                        # :183-188
+        for rerun_config, backup_linesearch_config in rerun_config_tuples:            # :191
+            if rets[-1].status != "success":
+                rets.append(attempt(DeviceStart(live[-1]), rerun_config, backup_linesearch_config))   # :195-200
+            else:
+                break                                                                 # :203
+    except BaseException:
+        for ws in live:
+            ws.close()
+        raise
+    for r in rets[:-1]:
+        r.workspace = None
+    if keep:
+        rets[-1].workspace = live[-1]
+    else:
+        live[-1].close()
+        rets[-1].workspace = None
     return rets

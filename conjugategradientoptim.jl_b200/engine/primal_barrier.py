@@ -118,6 +118,7 @@ def primalbarriermethod_(constraints: CvxInequalityConstraint, f0df0_, hdh_: Box
     N_constraints = getNconstraints(constraints)                   # :176
     x = np.array(x_initial, dtype=np.float64)                      # :179
     rets: List[List[Results]] = [None] * max_iters                 # :184
+    live = []                                                      # device workspaces kept for DeviceStart
 
     fdf_ = make_barrier(f0df0_, hdh_.lbs, hdh_.ubs, 1.0)           # (t is set below)  :205-213
     try:
@@ -125,17 +126,45 @@ def primalbarriermethod_(constraints: CvxInequalityConstraint, f0df0_, hdh_: Box
         if fdf_.infeasible_count(x) > 0:
             return assembleresults_(rets, "infeasible_start", 0, t_initial)
         t = verifyt0(t_initial, x, f0df0_, barrier_growth_factor, inf_f0_lb)   # :200
+        # every centering step starts from a vector that is already on the device: x_initial (the reference
+        # restarts from it every time, :217) is uploaded ONCE into a workspace that is never stepped, the minimiser
+        # of the previous step (update_iterate) stays in that step's workspace — DeviceStart, no H2D per step
+        device_start = hasattr(fdf_, "make_workspace") and hasattr(fdf_, "h")
+        start = x
+        if device_start:
+            from ..device import DeviceStart
+            fdf_.set_t(t)
+            anchor = fdf_.make_workspace(x, fuse_direction=False)
+            live.append(anchor)
+            start = DeviceStart(anchor)
         for i in range(1, max_iters + 1):                           # :215
             fdf_.set_t(t)
-            rets[i - 1] = minimizeobjectivererun(fdf_, x, centering_config, linesearch_config,   # :217-223
-                                                 *rerun_config_tuples, **kw)
+            rets[i - 1] = minimizeobjectivererun(fdf_, start, centering_config, linesearch_config,   # :217-223
+                                                 *rerun_config_tuples, keep_workspace=device_start and update_iterate, **kw)
             if rets[i - 1][-1].status != "success":                 # :224-232
                 return assembleresults_(rets, "centering_step_issue", i, t)
             if N_constraints / t < barrier_tol:                     # :235-243
                 return assembleresults_(rets, "success", i, t)
             if update_iterate:
-                x = np.array(rets[i - 1][-1].minimizer, dtype=np.float64)
+                if device_start:
+                    ws = rets[i - 1][-1].workspace
+                    rets[i - 1][-1].workspace = None
+                    for old in live:
+                        old.close()
+                    live[:] = [ws]
+                    start = DeviceStart(ws)
+                else:
+                    start = np.array(rets[i - 1][-1].minimizer, dtype=np.float64)
             t = barrier_growth_factor * t                           # :246
         return assembleresults_(rets, "max_iters_reached", max_iters, t)   # :249-254
     finally:
+        for ws in live:
+            ws.close()
+        for rr in rets:
+            if rr:
+                for r_ in rr:
+                    w_ = getattr(r_, "workspace", None)
+                    if w_ is not None:
+                        w_.close()
+                        r_.workspace = None
         fdf_.close()

@@ -173,6 +173,12 @@ int cgo_obj_spmv(cgo_obj *obj, int transposed, const double *x_host, double *y_h
  * f and g there): out[CGO_P_PHI] = f(x0), out[CGO_P_GPGP] = ‖g‖². */
 int cgo_state_create(cgo_ctx *ctx, cgo_obj *obj, const double *x0_host, int32_t lbfgs_m,
                      cgo_state **out_state, double out[CGO_PACK_LEN]);
+/* the same with x0 = vector `which` (0 x, 1 g, 2 u, 3 xp, 4 g⁺) of a live state of the same dimension: the restart
+ * of minimizeobjectivererun (optim.jl:191-201: the next attempt starts from rets[end].minimizer) and the centering
+ * steps of primalbarriermethod! (primal_barrier.jl:215-247) without a host round trip — one D2D copy, no H2D.
+ * `obj` may differ from the source state's objective (the barrier objective changes t between steps). */
+int cgo_state_create_from_state(cgo_ctx *ctx, cgo_obj *obj, cgo_state *src, int32_t which, int32_t lbfgs_m,
+                                cgo_state **out_state, double out[CGO_PACK_LEN]);
 int cgo_state_destroy(cgo_state *st);
 /* initializeLineSearchContainer! (cg_flavours.jl:22-35) and wolfe.jl:129: u = −g.
  * out[CGO_D_GU], out[CGO_D_UU]. */

@@ -68,3 +68,38 @@ def assert_same_run(ret, ora, exact=True, rtol=0.0, what=""):
     else:
         np.testing.assert_allclose(t.objective, ora.trace_objective, rtol=rtol)
         np.testing.assert_allclose(t.grad_norm, ora.trace_grad_norm, rtol=rtol)
+
+
+def record_gate(name, **numbers):
+    """Append the measured numbers of a tolerance gate to gpurun_out/north_star_gates.jsonl (brought back from the
+    GPU box; the committed copy is profiles/r2_north_star_gates.jsonl, quoted in DESIGN.md §3)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    rec = {"gate": name}
+    rec.update({k: (float(v) if isinstance(v, (np.floating, float)) else (int(v) if isinstance(v, (np.integer, int)) else v))
+                for k, v in numbers.items()})
+    with open(os.path.join(root, "gpurun_out", "north_star_gates.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+    print("GATE", json.dumps(rec))
+
+
+def gate_numbers(ret, ora, ora2, m):
+    """north_star's 1e-10 gate, measured: `window` = leading iterations on which two legitimate reference summation
+    orders (ora: sequential, ora2: compensated) agree to 2.5e-11; max relative deviation of the device run from the
+    sequential oracle inside the window, at iteration m, and overall over the first m iterations."""
+    rel = lambda a, b: np.abs(np.asarray(a) / np.asarray(b) - 1.0)
+    drift = np.maximum(rel(ora.trace_objective[:m], ora2.trace_objective[:m]), rel(ora.trace_grad_norm[:m], ora2.trace_grad_norm[:m]))
+    bad = np.nonzero(drift > 2.5e-11)[0]
+    w = int(bad[0]) if bad.size else m
+    df, dg = rel(ret.trace.objective[:m], ora.trace_objective[:m]), rel(ret.trace.grad_norm[:m], ora.trace_grad_norm[:m])
+    return w, dict(window=w, iterations_compared=m,
+                   f_maxrel_in_window=df[:w].max(), g_maxrel_in_window=dg[:w].max(),
+                   f_rel_at_last=df[m - 1], g_rel_at_last=dg[m - 1], f_maxrel_all=df.max(), g_maxrel_all=dg.max(),
+                   reference_orders_f_rel_at_last=rel(ora.trace_objective[:m], ora2.trace_objective[:m])[m - 1],
+                   reference_orders_g_rel_at_last=rel(ora.trace_grad_norm[:m], ora2.trace_grad_norm[:m])[m - 1],
+                   decisions_identical=bool(np.array_equal(ret.trace.step_size[:m], ora.trace_step_size[:m])
+                                            and np.array_equal(ret.trace.objective_evals[:m], ora.trace_objective_evals[:m])),
+                   iters_device=int(ret.iters_ran), iters_oracle_seq=int(ora.iters_ran), iters_oracle_comp=int(ora2.iters_ran),
+                   final_f_rel=abs(ret.objective - ora.objective) / max(abs(ora.objective), 1e-300))

@@ -56,6 +56,8 @@ class NumpyWorkspace:
         self.fuse_direction = fuse_direction
         self.sm = obj.sum_mode
         self.site = self.o.trial_site()
+        if hasattr(x_initial, "ws"):          # DeviceStart: the iterate of a live workspace
+            x_initial = x_initial.ws.x_
         self.x_ = np.array(x_initial, dtype=np.float64)
         f, g = self.o.fdf(self.x_)
         self.g_ = g

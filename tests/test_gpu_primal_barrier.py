@@ -91,6 +91,8 @@ def test_primal_barrier_method_matches_oracle(ctx, update):
                                 pair[1], pair[2], cg.setupPrimalBarrierConfig(1e-2 * n, 20.0, 8, t_initial=1.0),
                                 update_iterate=update)
     assert b.status == ob.status and b.iters_ran == ob.iters_ran and b.t_final == ob.t_final
+    # device-resident restarts: no centering step (and no rerun attempt) uploads its starting point
+    assert all(r.h2d_bytes == 0 and r.workspace is None for step in b.centering_results for r in step)
     for step, ostep in zip(b.centering_results, ob.centering_results):
         assert [r.status for r in step] == [o.status for o in ostep]
         assert abs(step[-1].iters_ran - ostep[-1].iters_ran) <= 2
@@ -105,3 +107,25 @@ def test_primal_barrier_method_matches_oracle(ctx, update):
     t0 = cg.verifyt0(float("nan"), np.zeros(n), f0, 20.0, 0.0)
     assert t0 == O.Objective.rosenbrock(n).fdf(np.zeros(n))[0] * 20.0 or abs(t0 - n / 2 * 20.0) < 1e-9
     f0.close()
+
+
+def test_rerun_starts_on_the_device(ctx):
+    """minimizeobjectivererun (optim.jl:173-208): the second attempt starts from the first one's minimiser on the
+    device (DeviceStart, one D2D copy) and gives bit for bit what a restart from the downloaded host copy gives."""
+    n = 4096
+    obj = cg.RosenbrockGPU(n, ctx)
+    x0 = obj.default_x0(24, 0.1)
+    _, cfg1, ls1 = make_pair("HagerZhang", "StrongWolfeBisection", max_iters=7)          # ends :max_iters_reached
+    _, cfg2, ls2 = make_pair("LiuStorrey", "Wolfe", max_iters=40)
+    rets = cg.minimizeobjectivererun(obj, x0, cfg1, ls1, (cfg2, ls2))
+    assert len(rets) == 2 and rets[0].status == "max_iters_reached"
+    assert rets[0].h2d_bytes == 8 * n and rets[1].h2d_bytes == 0
+    a = cg.minimizeobjective(obj, x0, cfg1, ls1)
+    b = cg.minimizeobjective(obj, a.minimizer, cfg2, ls2)                               # the host round trip
+    assert np.array_equal(rets[0].minimizer, a.minimizer) and rets[1].status == b.status
+    assert np.array_equal(rets[1].trace.objective, b.trace.objective) and np.array_equal(rets[1].minimizer, b.minimizer)
+    ws = obj.make_workspace(x0)
+    c = cg.minimizeobjective(obj, cg.DeviceStart(ws), cfg1, ls1)                        # DeviceStart by hand
+    ws.close()
+    assert c.h2d_bytes == 0 and np.array_equal(c.minimizer, a.minimizer)
+    obj.close()

@@ -2,13 +2,15 @@
 (BASELINE.json configs[2]): generator, explicit transpose, SpMV / SpMVᵀ kernels, the fused trial
 pack and whole CG runs, all BIT-EXACT against the oracle in canonical-order mode; plus
 size-independent properties at the full n = 2e8."""
+import os
+
 import numpy as np
 import pytest
 
 import cgoptim_b200 as cg
 from oracle import oracle as O
 
-from helpers import FLAVOURS, assert_same_run, make_pair
+from helpers import gate_numbers, record_gate, FLAVOURS, assert_same_run, make_pair
 from numpy_workspace import NumpyObjective
 
 pytestmark = pytest.mark.gpu
@@ -159,10 +161,8 @@ def test_north_star_gates_vs_reference_shaped_oracle(ctx):
     ocfg2, _, _ = make_pair("HagerZhang", sum_mode="comp", beta_form="literal", max_iters=400)
     ora2 = O.minimize(O.Objective.sparse_ls(n, 10, 8192, 24, 0), np.zeros(n), ocfg2)
     m = min(50, len(ora.trace_objective), len(ora2.trace_objective))
-    drift = np.maximum(np.abs(ora.trace_objective[:m] / ora2.trace_objective[:m] - 1),
-                       np.abs(ora.trace_grad_norm[:m] / ora2.trace_grad_norm[:m] - 1))
-    bad = np.nonzero(drift > 2.5e-11)[0]
-    w = int(bad[0]) if bad.size else m
+    w, nums = gate_numbers(ret, ora, ora2, m)
+    record_gate("sparse least squares n=5e4 coh 0, HZ + StrongWolfe, device vs reference-shaped oracle", **nums)
     assert w >= 10
     np.testing.assert_allclose(ret.trace.objective[:w], ora.trace_objective[:w], rtol=1e-10)
     np.testing.assert_allclose(ret.trace.grad_norm[:w], ora.trace_grad_norm[:w], rtol=1e-10)
@@ -222,6 +222,23 @@ def test_large_n_properties(ctx, n):
     r2 = cg.minimizeobjective(obj, np.zeros(n), cfg, ls)
     assert np.all(np.diff(r1.trace.objective) < 0)
     assert np.array_equal(r1.trace.objective, r2.trace.objective) and np.array_equal(r1.minimizer, r2.minimizer)
+    obj.close()
+
+
+@pytest.mark.parametrize("coh", [0, 30])
+def test_oracle_compared_run_n2e7(ctx, coh):
+    """A run at a tenth of the full size (n = 2e7, 2e8 nonzeros: 264 tiles per persistent CTA, the lockstep window,
+    the dynamic slice queue, multi-tile reductions) against the oracle in the canonical order, bit for bit: five
+    iterations, both matrix variants (coh 0: k_spmv_direct + BLAS-1 dots; coh 30: fused k_csr_rows)."""
+    n = 20_000_000
+    ocfg, cfg, ls = make_pair("HagerZhang", max_iters=5, sum_mode="cgo")
+    obj = cg.SparseLSGPU(n, 10, None, 24, coh, ctx)
+    ora_obj = O.Objective.sparse_ls(n, 10, None, 24, coh, threads=os.cpu_count() or 1)
+    assert ora_obj.trial_site() == obj.trial_site
+    ora = O.minimize(ora_obj, np.zeros(n), ocfg)
+    ret = cg.minimizeobjective(obj, np.zeros(n), cfg, ls)
+    assert ora.iters_ran == 5
+    assert_same_run(ret, ora, what=f"n=2e7 coh={coh}")
     obj.close()
 
 
