@@ -59,6 +59,7 @@ _SIGS = {
     "cgo_host_free": (C.c_int, [_vp]),
     "cgo_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cgo_obj_rosenbrock_create": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
+    "cgo_obj_rosenbrock_chained_create": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "cgo_obj_sparse_ls_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(_vp)]),
     "cgo_obj_sparse_ls_create_csr": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "cgo_obj_logreg_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.POINTER(_vp)]),

@@ -547,6 +547,133 @@ struct RosenObj : cgo_obj {
     }
 };
 
+// ------------------------------------------------------------------ chained Rosenbrock
+// The reference's own Rosenbrock, rosenbrockfunc (examples/helpers/test_funcs.jl:50-57):
+//   f = Σ_{i<d} (1 − x_i)² + 100 (x_{i+1} − x_i²)²,
+//   g_i = 200 (x_i − x_{i−1}²) [i > 1] − 2 (1 − x_i) − 400 x_i (x_{i+1} − x_i²) [i < d]      (SURVEY.md §8d cfg 1).
+// Elements couple to both neighbours, so one trial is two kernels, like the CSR objectives: K_a xp = x + a u
+// (AxpyDir; sharded: pushes the two boundary elements into the ring neighbours' halos) and this one, which reads
+// xp with its ±1 neighbours and reduces f, dϕ, ‖g⁺‖² and the getβ dots.  Arithmetic as oracle rosen_chained_fdf.
+struct RosenChainedEval {
+    static constexpr int TCLASS = CGO_T_TRIAL;
+    static constexpr int K = 9;
+    static constexpr int OCC = 2;
+    struct In { double2 p, u, g; double pm, pn; };
+    const double *xp;               // local origin; xp[−1] and xp[n] are halo (sharded) or never read (the ends)
+    const double2 *u, *g;
+    double2 *gp;
+    int64_t offset, n_global, n_local;
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ In load(int64_t q) const {
+        In r;
+        r.p = cgo_ld2((const double2 *)xp + q);
+        r.u = cgo_ld2(u + q); r.g = cgo_ld2(g + q);
+        const int64_t i0 = 2 * q, i1 = 2 * q + 1;
+        r.pm = offset + i0 > 0 ? __ldg(xp + i0 - 1) : 0.0;
+        r.pn = offset + i1 + 1 < n_global ? __ldg(xp + i1 + 1) : 0.0;
+        return r;
+    }
+    __device__ __forceinline__ void dots(double gn, double gg, double uu, double (&acc)[K]) const {
+        const double y = gn - gg;
+        acc[CGO_P_DPHI] = acc[CGO_P_DPHI] + gn * uu;
+        acc[CGO_P_GPGP] = acc[CGO_P_GPGP] + gn * gn;
+        acc[CGO_P_YY] = acc[CGO_P_YY] + y * y;
+        acc[CGO_P_UY] = acc[CGO_P_UY] + uu * y;
+        acc[CGO_P_YGP] = acc[CGO_P_YGP] + y * gn;
+        acc[CGO_P_GPG] = acc[CGO_P_GPG] + gn * gg;
+        acc[CGO_P_UG] = acc[CGO_P_UG] + uu * gg;
+        acc[CGO_P_UU] = acc[CGO_P_UU] + uu * uu;
+    }
+    __device__ __forceinline__ void apply(int64_t q, const In &in, double (&acc)[K], bool v2) const {
+        const int64_t gi0 = offset + 2 * q, gi1 = gi0 + 1;
+        const double x0 = in.p.x, x1 = in.p.y;
+        const double tm = x0 - in.pm * in.pm;               // t_{i0−1}
+        const double t0 = x1 - x0 * x0;                     // t_{i0}
+        const double t1 = in.pn - x1 * x1;                  // t_{i1}
+        const double om0 = 1.0 - x0, om1 = 1.0 - x1;
+        double2 gn;
+        double g0 = 0.0, f0 = 0.0;
+        if (gi0 > 0) g0 = g0 + 200.0 * tm;
+        if (gi0 < n_global - 1) { g0 = g0 + (-2.0 * om0 - (400.0 * x0) * t0); f0 = om0 * om0 + (100.0 * t0) * t0; }
+        gn.x = g0;
+        acc[CGO_P_PHI] = acc[CGO_P_PHI] + f0;
+        dots(g0, in.g.x, in.u.x, acc);
+        gn.y = 0.0;
+        if (v2) {
+            double g1 = 0.0, f1 = 0.0;
+            g1 = g1 + 200.0 * t0;                           // gi1 > 0 always
+            if (gi1 < n_global - 1) { g1 = g1 + (-2.0 * om1 - (400.0 * x1) * t1); f1 = om1 * om1 + (100.0 * t1) * t1; }
+            gn.y = g1;
+            acc[CGO_P_PHI] = acc[CGO_P_PHI] + f1;
+            dots(g1, in.g.y, in.u.y, acc);
+        }
+        cgo_st2(gp + q, gn);
+    }
+};
+
+struct RosenChainedObj : cgo_obj {
+    int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        const int R = ctx->nranks, me = ctx->rank;
+        RedArgs red = cgo_red_args(ctx, CGO_P_PHI);
+        if (R > 1 && st->peer_x) {
+            const int prev = (me + R - 1) % R, next = (me + 1) % R;
+            const unsigned long long e = ++ctx->epoch;
+            unsigned long long *fprev = (unsigned long long *)ctx->flags_peer[(size_t)prev];
+            unsigned long long *fnext = (unsigned long long *)ctx->flags_peer[(size_t)next];
+            int64_t plo, phi;
+            CGO_TRY(cgo_shard_range(n_global, R, prev, 2, &plo, &phi));
+            HaloPush hp;
+            hp.prev_right = (double *)st->xpeers[st->xp_alloc][(size_t)prev] + halo + (phi - plo);
+            hp.next_left = (double *)st->xpeers[st->xp_alloc][(size_t)next];
+            hp.sig_prev = fprev + CGO_F_XP_FROM_NEXT;
+            hp.sig_next = fnext + CGO_F_XP_FROM_PREV;
+            hp.epoch = e;
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta, &hp));                         // K_a + halo push
+            red.wait0 = ctx->flags_local + CGO_F_XP_FROM_PREV; red.wait1 = ctx->flags_local + CGO_F_XP_FROM_NEXT;
+            red.wait_val = e;
+        } else {
+            CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                              // K_a
+            if (R > 1) CGO_TRY(cgo_sendrecv_ring(ctx, st->xp, st->xp + st->n, st->xp + st->n - halo, st->xp - halo, halo));
+        }
+        RosenChainedEval op;
+        op.xp = st->xp; op.u = (const double2 *)st->u; op.g = (const double2 *)st->g; op.gp = (double2 *)st->gp;
+        op.offset = offset; op.n_global = n_global; op.n_local = st->n;
+        CGO_TRY(launch_blas1(ctx, op, st->n, red));
+        return cgo_finish_pack(ctx, 12, out);
+    }
+    // K_a R x,u W xp (+ R g, W u on the first trial of an iteration) | R xp,u,g W g⁺
+    double bytes_per_eval() const override { return 8.0 * 7.0 * (double)n_local; }
+    void reduction_site(int32_t *V, int32_t *U) const override { *V = 2; *U = CGO_U_VEC; }
+    int default_x0(uint64_t seed, double perturb, double *x0) override {
+        for (int64_t i = 0; i < n_local; ++i) {
+            int64_t gi = offset + i;
+            double base = (gi % 2 == 0) ? -1.2 : 1.0;
+            x0[i] = perturb != 0.0 ? base + perturb * (2.0 * cgo_host_u01(seed, (uint64_t)gi, 0) - 1.0) : base;
+        }
+        return 0;
+    }
+};
+extern "C" int cgo_obj_rosenbrock_chained_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out) {
+    CGO_CHECK(ctx && out, "NULL argument");
+    CGO_CHECK(n_global >= 2 && n_global % 2 == 0, "chained Rosenbrock: need an even n >= 2 (got %lld)", (long long)n_global);
+    CGO_CHECK(ctx->nranks == 1 || n_global >= 4 * ctx->nranks, "chained Rosenbrock: %d ranks need n >= %d", ctx->nranks, 4 * ctx->nranks);
+    int64_t lo, hi;
+    CGO_TRY(cgo_shard_range(n_global, ctx->nranks, ctx->rank, 2, &lo, &hi));
+    RosenChainedObj *o = new RosenChainedObj();
+    o->ctx = ctx;
+    o->n_global = n_global;
+    o->offset = lo;
+    o->n_local = hi - lo;
+    o->halo = ctx->nranks > 1 ? 2 : 0;           // ±1 neighbour, kept even (16-byte alignment)
+    for (int q = 0; q < ctx->nranks; ++q) {
+        int64_t a, b;
+        cgo_shard_range(n_global, ctx->nranks, q, 2, &a, &b);
+        if (b - a > o->n_alloc) o->n_alloc = b - a;
+    }
+    *out = o;
+    return 0;
+}
+
 extern "C" int cgo_obj_rosenbrock_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out) {
     CGO_CHECK(ctx && out, "NULL argument");
     CGO_CHECK(n_global >= 2 && n_global % 2 == 0, "extended Rosenbrock needs an even n >= 2 (got %lld)", (long long)n_global);

@@ -217,6 +217,14 @@ def RosenbrockGPU(n: int, ctx: Optional[Context] = None) -> DeviceObjective:
     return DeviceObjective(ctx, h)
 
 
+def RosenbrockChainedGPU(n: int, ctx: Optional[Context] = None) -> DeviceObjective:
+    """The reference's own chained Rosenbrock (examples/helpers/test_funcs.jl:50-57) with its gradient."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    check(lib().cgo_obj_rosenbrock_chained_create(ctx.h, n, C.byref(h)))
+    return DeviceObjective(ctx, h)
+
+
 def SparseLSGPU(n: int, nnz_per_row: int = 10, W: Optional[int] = None, seed: int = 24,
                 coh_log2: int = 0, ctx: Optional[Context] = None) -> DeviceObjective:
     """½‖Ax − b‖² with the synthetic banded-random CSR of SURVEY.md §8d cfg 3."""

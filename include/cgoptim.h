@@ -128,6 +128,10 @@ int cgo_shard_range(int64_t n, int nranks, int rank, int64_t align, int64_t *lo,
  * cg_utils.jl:18).  With a communicator on the ctx the constructors build this rank's shard. */
 /* extended Rosenbrock (pairs) f = Σ 100 (x_{2i} − x_{2i−1}²)² + (1 − x_{2i−1})², n_global even */
 int cgo_obj_rosenbrock_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out);
+/* the reference's own chained Rosenbrock, rosenbrockfunc of examples/helpers/test_funcs.jl:50-57 with its
+ * hand-derived gradient (SURVEY.md §8d cfg 1): f = Σ_{i<n} (1 − x_i)² + 100 (x_{i+1} − x_i²)²; sharded runs keep a
+ * ±1 halo of the trial point, pushed over peer memory by the kernel that forms it.  n_global even. */
+int cgo_obj_rosenbrock_chained_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out);
 /* ½‖Ax − b‖², A n×n banded-random CSR generated on device (generator spec: DESIGN.md §objectives;
  * restated in oracle/cgo_oracle.c orc_obj_sparse_ls_synth), b = A x_true. */
 int cgo_obj_sparse_ls_create_synthetic(cgo_ctx *ctx, int64_t n_global, int32_t nnz_per_row,

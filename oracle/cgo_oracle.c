@@ -290,6 +290,13 @@ static double rosen_chained_fdf(orc_objective *o, double *g, const double *x) {
         g[i] += -2.0 * om - (400.0 * x[i]) * t;
         g[i + 1] += 200.0 * t;
     }
+    /* canonical order: the device kernel (blas1.cu RosenChainedEval) reads double2 and adds the terms of both
+     * elements lane by lane (V = 2, U = 4), one term per ELEMENT with a +0.0 for the last one, so that the shards
+     * of the sum are the shards of the vector */
+    if (o->sum_mode == ORC_SUM_CGO) {
+        fp[d - 1] = 0.0;
+        return cgo_reduce(sum_term, fp, d, 2, g_blas1_U, 2);
+    }
     return orc_sum(fp, d - 1, o->sum_mode, 1);
 }
 

@@ -18,6 +18,16 @@ from oracle import oracle as O  # noqa: E402
 from helpers import make_pair  # noqa: E402
 
 
+def sources_sha():
+    """what a log of this worker vouches for: the worker itself and every CUDA source of libcgoptim.so"""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in [os.path.abspath(__file__)] + sorted(glob.glob(os.path.join(ROOT, "conjugategradientoptim.jl_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -29,6 +39,7 @@ def main():
     fails = []
     if rank == 0:
         print(f"PEER_MEMORY={int(ctx.peer_memory)}", flush=True)
+        print(f"WORLD={world} SOURCES_SHA={sources_sha()}", flush=True)
 
     def check(name, obj, x0_full, ora_obj, flavour, max_iters):
         ocfg, cfg, ls = make_pair(flavour, max_iters=max_iters)
@@ -51,6 +62,11 @@ def main():
     for flavour in ("HagerZhang", "LBFGS"):
         obj = cg.RosenbrockGPU(n, ctx)
         check("rosenbrock", obj, O.rosenbrock_x0(n, 24, 0.1), O.Objective.rosenbrock(n), flavour, 40)
+        obj.close()
+    # the reference's own chained Rosenbrock (examples/helpers/test_funcs.jl:50-57): ±1 halo of the trial point
+    for flavour in ("HagerZhang", "LBFGS"):
+        obj = cg.RosenbrockChainedGPU(n, ctx)
+        check("rosenbrock_chained", obj, O.rosenbrock_x0(n, 24, 0.1), O.Objective.rosenbrock_chained(n), flavour, 40)
         obj.close()
     for coh in (0, 30):
         for flavour in ("HagerZhang", "LBFGS"):

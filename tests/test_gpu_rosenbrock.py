@@ -112,6 +112,32 @@ def test_literal_beta_bit_exact(ctx, flavour):
     assert_same_run(ret, ora, what=flavour)
 
 
+@pytest.mark.parametrize("n,flavour,linesearch", [(2, "HagerZhang", "StrongWolfeBisection"), (10, "LiuStorrey", "Wolfe"),
+                                                  (10_000, "HagerZhang", "StrongWolfeBisection"),
+                                                  (10_000, "LBFGS", "StrongWolfeBisection"),
+                                                  (1_000_002, "YuanWangSheng", "StrongWolfeBisection")])
+def test_chained_rosenbrock_bit_exact(ctx, n, flavour, linesearch):
+    """The reference's own Rosenbrock — rosenbrockfunc, examples/helpers/test_funcs.jl:50-57, with the gradient of
+    SURVEY.md §8d cfg 1 — on the device (two kernels per trial: xp, then f / g⁺ / dots with the ±1 neighbours),
+    whole traces bit for bit against oracle rosen_chained_fdf, fused and unfused direction update."""
+    ocfg, cfg, ls = make_pair(flavour, linesearch, max_iters=60 if n > 100 else 1000)
+    obj = cg.RosenbrockChainedGPU(n, ctx)
+    assert obj.trial_site == (2, 4)
+    x0 = obj.default_x0(24, 0.1 if n > 2 else 0.0)
+    ora_obj = O.Objective.rosenbrock_chained(n)
+    ws = obj.make_workspace(x0, fuse_direction=False)
+    ora_obj.set_sum_mode("cgo")
+    f, g = ora_obj.fdf(x0)
+    assert ws.f_x0 == f and np.array_equal(ws.download()[1], g)
+    ws.close()
+    ora = O.minimize(O.Objective.rosenbrock_chained(n), x0, ocfg)
+    ret = cg.minimizeobjective(obj, x0, cfg, ls)
+    assert_same_run(ret, ora, what=f"chained n={n} {flavour}")
+    ret2 = cg.minimizeobjective(obj, x0, cfg, ls, fuse_direction=False)
+    assert np.array_equal(ret.trace.objective, ret2.trace.objective) and np.array_equal(ret.minimizer, ret2.minimizer)
+    obj.close()
+
+
 def test_north_star_gates_vs_reference_shaped_oracle(ctx):
     """The fused GPU path against the oracle in the reference's own shape (sequential sums,
     literal β).  north_star's gates: f and ‖g‖ within 1e-10 relative, identical step sizes and
