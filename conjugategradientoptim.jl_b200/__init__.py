@@ -11,7 +11,7 @@ from .cg_types import (CGConfig, CGβConfig, DisableTrace, EnableTrace, LineSear
                        βConfig)
 from .cg_flavours import (HagerZhang, LiuStorrey, SallehAlhawarat, YuanWangSheng, getβ,  # noqa: F401
                           initializeLineSearchContainer_, initializeβ, updatedir_)
-from .qn_flavours import LBFGS  # noqa: F401
+from .qn_flavours import LBFGS, BroydenFamily, setupBroydenFamily  # noqa: F401
 from .cg_utils import evalϕdϕ_  # noqa: F401
 from .linesearch import (Armijo, Backtracking, StrongWolfeBisection, Wolfe, WolfeBisection,  # noqa: F401
                          YuanWeiLuWolfe, setupStrongWolfeBisection)
@@ -21,6 +21,6 @@ from .engine import (BoxConstraint, CvxInequalityConstraint, LinesearchSolveSys,
                      setupLinesearchSolveSys, setupPrimalBarrierConfig, solvesystem, verifyt0)
 from .engine.optim import linesearch_  # noqa: F401
 from .device import (Context, DeviceLineSearchContainer, DeviceObjective, DeviceStart, DeviceVector,  # noqa: F401
-                     BoxBarrierGPU, LogRegGPU, RosenbrockChainedGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, default_context,
+                     BoxBarrierGPU, LogRegGPU, RosenbrockChainedGPU, RosenbrockGPU, SparseLSGPU, SparseLSGPU_from_csr, UserObjectiveGPU, default_context,
                      dot, shard_range, BatchedResults, minimizeobjective_batched, batched_lanes)
 from .device import DeviceLineSearchContainer as LineSearchContainer  # noqa: F401

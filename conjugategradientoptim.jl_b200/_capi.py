@@ -34,6 +34,7 @@ class BatchedConfig(C.Structure):
     ]
 
 
+USER_FDF = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 _SIGS = {
@@ -47,6 +48,7 @@ _SIGS = {
     "cgo_ctx_set_gather_block_bytes": (C.c_int, [_vp, C.c_int64]),
     "cgo_ctx_set_sweep_window": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_set_csr_mode": (C.c_int, [_vp, C.c_int]),
+    "cgo_ctx_trim_pools": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_sm_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cgo_ctx_kernel_launches": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_timing": (C.c_int, [_vp, C.c_int]),
@@ -58,6 +60,7 @@ _SIGS = {
     "cgo_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "cgo_host_free": (C.c_int, [_vp]),
     "cgo_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cgo_obj_user_create": (C.c_int, [_vp, C.c_int64, USER_FDF, _vp, C.POINTER(_vp)]),
     "cgo_obj_rosenbrock_create": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "cgo_obj_rosenbrock_chained_create": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "cgo_obj_sparse_ls_create_synthetic": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(_vp)]),

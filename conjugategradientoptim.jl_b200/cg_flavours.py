@@ -111,7 +111,9 @@ def getβ(β_config, g_next, g, u):
             numerator = f64(P[P_YGP])                                   # :166
             denominator = -f64(P[P_UY])                                 # :167
             return numerator / denominator
-    from .qn_flavours import LBFGS, getβ_lbfgs
+    from .qn_flavours import LBFGS, BroydenFamily, getβ_lbfgs
     if isinstance(β_config, LBFGS):
         return getβ_lbfgs(β_config, ws)
+    if isinstance(β_config, BroydenFamily):
+        return f64(0.0)             # B never leaves the identity (qn_flavours.jl:81): u = −g
     raise TypeError(f"no getβ method for {type(β_config).__name__}")

@@ -547,6 +547,52 @@ struct RosenObj : cgo_obj {
     }
 };
 
+// ------------------------------------------------------------------ user objective
+// The reference takes ANY fdf!(g, x) -> f (src/engine/optim.jl:6-11, :25; src/cg_utils.jl:18).  On the device that
+// callback is a host function that ENQUEUES, on the ctx stream, whatever computes g⁺ = ∇f(xp) and f from the
+// trial point (its own kernels, cuBLAS / cuSPARSE calls, a framework's ops): cgo_user_fdf.  The library does the
+// rest of evalϕdϕ! and of getβ around it: K_a xp = x + a u [after updatedir!], then the callback, then one BLAS-1
+// pass for dϕ = g⁺·u, ‖g⁺‖² and the getβ dots (GradDots).  Two kernels of the library per trial + the user's.
+__global__ void k_scalar_to_pack(const double *src, double *dst) { *dst = *src; }
+struct UserObj : cgo_obj {
+    cgo_user_fdf fn = nullptr;
+    void *user = nullptr;
+    double *d_f = nullptr;
+    ~UserObj() override {
+        if (ctx && cgo_ctx_alive(ctx)) cudaSetDevice(ctx->device);
+        cudaFree(d_f);
+    }
+    int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        CGO_TRY(cgo_blas1_axpy_dir(st, a, fused, beta));                                  // K_a
+        const int rc = fn(user, (void *)ctx->stream, st->n, offset, st->xp, st->gp, d_f);
+        CGO_CHECK(rc == 0, "user objective callback returned %d", rc);
+        k_scalar_to_pack<<<1, 1, 0, ctx->stream>>>(d_f, cgo_red_args(ctx, CGO_P_PHI).out);  // this rank's part of f
+        ctx->launches++;
+        CGO_CUDA(cudaGetLastError());
+        CGO_TRY(cgo_blas1_grad_dots(st));
+        return cgo_finish_pack(ctx, 12, out);
+    }
+    double bytes_per_eval() const override { return 8.0 * 6.0 * (double)n_local; }   // K_a 24n + dots 24n (+ the user's)
+    void reduction_site(int32_t *V, int32_t *U) const override { *V = 2; *U = CGO_U_VEC; }
+    int default_x0(uint64_t, double, double *x0) override {
+        for (int64_t i = 0; i < n_local; ++i) x0[i] = 0.0;
+        return 0;
+    }
+};
+extern "C" int cgo_obj_user_create(cgo_ctx *ctx, int64_t n_global, cgo_user_fdf fdf, void *user, cgo_obj **out) {
+    CGO_CHECK(ctx && fdf && out, "NULL argument");
+    CGO_CHECK(n_global >= 2 && n_global % 2 == 0, "user objective: need an even n >= 2 (got %lld; pad with a fixed coordinate)", (long long)n_global);
+    CGO_CUDA(cudaSetDevice(ctx->device));
+    int64_t lo, hi;
+    CGO_TRY(cgo_shard_range(n_global, ctx->nranks, ctx->rank, 2, &lo, &hi));
+    UserObj *o = new UserObj();
+    o->ctx = ctx; o->fn = fdf; o->user = user;
+    o->n_global = n_global; o->offset = lo; o->n_local = hi - lo;
+    if (cudaMalloc(&o->d_f, sizeof(double)) != cudaSuccess) { delete o; cgo_set_error("cudaMalloc failed"); return 1; }
+    *out = o;
+    return 0;
+}
+
 // ------------------------------------------------------------------ chained Rosenbrock
 // The reference's own Rosenbrock, rosenbrockfunc (examples/helpers/test_funcs.jl:50-57):
 //   f = Σ_{i<d} (1 − x_i)² + 100 (x_{i+1} − x_i²)²,
@@ -1030,6 +1076,7 @@ extern "C" int cgo_accept(cgo_state *st) {
     std::swap(st->base[0], st->base[3]);
     std::swap(st->base[1], st->base[4]);
     st->xp_alloc ^= 1;
+    st->obj->on_accept(st);
     return 0;
 }
 

@@ -253,6 +253,23 @@ void cgo_dev_free(cgo_ctx *c, void *ptr, size_t bytes) {
     }
 }
 
+// release the device blocks the ctx keeps for reuse (up to 24 GB of state vectors of destroyed states); peer-mapped
+// blocks stay pooled (freeing them is a collective)
+extern "C" int cgo_ctx_trim_pools(cgo_ctx *c, int64_t *freed_bytes) {
+    CGO_CHECK(c != nullptr, "NULL ctx");
+    CGO_CUDA(cudaSetDevice(c->device));
+    CGO_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t freed = 0;
+    for (auto &kv : c->dev_pool) {
+        for (void *p : kv.second) { cudaFree(p); freed += (int64_t)kv.first; }
+        kv.second.clear();
+    }
+    c->dev_pool.clear();
+    c->dev_pool_bytes = 0;
+    if (freed_bytes) *freed_bytes = freed;
+    return 0;
+}
+
 // ------------------------------------------------------------------ peer memory (CUDA IPC)
 int cgo_peer_alloc(cgo_ctx *c, size_t bytes, void **local, std::vector<void *> &peers) {
     const int R = c->nranks;

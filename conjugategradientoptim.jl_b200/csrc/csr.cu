@@ -1258,6 +1258,11 @@ struct CsrObj : cgo_obj {
     double *b = nullptr;               // rhs (LS) or labels (logreg), nrows
     double *r_base = nullptr, *r = nullptr;   // residual / c vector with halo
     double *qv = nullptr;                     // v = A u of the quadratic-aware line search (nrows)
+    // whose residual `r` holds: every trial leaves r(xp) of its state; cgo_accept makes that r(x); the
+    // Hessian-vector product and trials of OTHER states on the same objective overwrite it
+    const cgo_state *r_state = nullptr;
+    bool r_at_xp = false, r_at_x = false;
+    int quad_steps = 0;                       // accepted steps since r was last formed as A x − b
     std::vector<void *> rpeers;               // peer mappings of r_base (sharded LS with peer memory)
     bool r_is_peer = false;
     double lambda = 0.0;
@@ -1425,6 +1430,7 @@ struct CsrObj : cgo_obj {
     }
     int hessvec_dir(cgo_state *st, double *out) override {
         CGO_CHECK(!logreg, "the Hessian-vector product is implemented for least squares");
+        r_state = nullptr; r_at_x = r_at_xp = false;                                      // r is scratch here
         CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
         if (direct()) {
             CGO_TRY(launch_direct(ctx, A, st->u, DirStore{r}, dir_args(ctx), CGO_T_SPMV));
@@ -1449,6 +1455,21 @@ struct CsrObj : cgo_obj {
             CGO_CUDA(cudaMalloc(&qv, sizeof(double) * (size_t)(nrows + CSR_PAD)));
             CGO_CUDA(cudaMemsetAsync(qv, 0, sizeof(double) * (size_t)(nrows + CSR_PAD), ctx->stream));
         }
+        // r must be the residual at THIS state's x.  It is after a trial of this state was accepted; it is not after
+        // a Hessian-vector product, after another state used the objective, or — the recursive update r += a v
+        // drifts by ≈ ε‖r₀‖ per step — after 64 accepted steps: then r = A x − b is formed again
+        if (!(r_state == st && r_at_x) || quad_steps >= 64) {
+            CGO_TRY(cgo_sendrecv_ring(ctx, st->x, st->x + st->n, st->x + st->n - halo, st->x - halo, halo));
+            if (direct()) {
+                DirResidual<false> f1{b, r, nullptr, nullptr, 0, nrows};
+                CGO_TRY(launch_direct(ctx, A, st->x, f1, dir_args(ctx), CGO_T_SPMV));
+            } else {
+                EpiResidualT<false> e0;
+                e0.b = b; e0.r = r; e0.prev_right = e0.next_left = nullptr; e0.halo = 0; e0.nrows = nrows;
+                CGO_TRY(launch_csr(ctx, A, st->x, e0, cgo_red_args(ctx, CGO_PACK_LEN - 1), CGO_T_SPMV));
+            }
+            r_state = st; r_at_x = true; r_at_xp = false; quad_steps = 0;
+        }
         CGO_TRY(cgo_sendrecv_ring(ctx, st->u, st->u + st->n, st->u + st->n - halo, st->u - halo, halo));
         if (direct()) {
             CGO_TRY(launch_direct(ctx, A, st->u, DirStore{qv}, dir_args(ctx), CGO_T_SPMV));
@@ -1461,6 +1482,8 @@ struct CsrObj : cgo_obj {
     }
     int quad_accept(cgo_state *st, double a, double *out) override {
         CGO_CHECK(!logreg && qv != nullptr, "cgo_quad_accept before cgo_quad_begin");
+        CGO_CHECK(r_state == st && r_at_x, "cgo_quad_accept: the residual of this state was overwritten since cgo_quad_begin");
+        r_at_x = false; r_at_xp = true; ++quad_steps;                                     // r becomes r(xp) below
         CGO_TRY(cgo_blas1_axpy_dir(st, a, false, 0.0));                                   // xp = x + a u
         CGO_TRY(cgo_blas1_residual_axpy(ctx, r, qv, a, nrows, CGO_P_PHI));                // r += a v, Σ r²
         CGO_TRY(exchange(r, nrows));
@@ -1477,7 +1500,13 @@ struct CsrObj : cgo_obj {
         out[CGO_P_PHI] = 0.5 * out[CGO_P_PHI];
         return 0;
     }
+    void on_accept(cgo_state *st) override {
+        r_at_x = (r_state == st) && r_at_xp;
+        r_at_xp = false;
+        if (r_state != st) r_state = nullptr;
+    }
     int eval_trial(cgo_state *st, double a, bool fused, double beta, double *out) override {
+        r_state = st; r_at_xp = true; r_at_x = false; quad_steps = 0;        // r = A xp − b (least squares) / c (logreg)
         if (!logreg && direct()) return eval_trial_ls_direct(st, a, fused, beta, out);
         if (!logreg && r_is_peer && st->peer_x) return eval_trial_ls_peer(st, a, fused, beta, out);
         if (logreg && lr_direct) return eval_trial_lr_direct(st, a, fused, beta, out);

@@ -172,6 +172,8 @@ struct cgo_obj {
     // quad_accept: xp = x + a u, r += a v, g⁺ = Aᵀ r and the usual pack (CGO_P_PHI = ½ Σ r²).
     virtual int quad_begin(cgo_state *st, double *out_host);
     virtual int quad_accept(cgo_state *st, double a, double *out_host);
+    // cgo_accept(st) adopted (xp, g⁺) as (x, g): objectives that keep per-trial state (the residual) take note
+    virtual void on_accept(cgo_state *) {}
     virtual double bytes_per_eval() const = 0;
     // canonical-order mapping (V, U) of the kernels that reduce this objective's trial dots (include/cgoptim.h)
     virtual void reduction_site(int32_t *V, int32_t *U) const = 0;

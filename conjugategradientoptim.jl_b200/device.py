@@ -41,6 +41,14 @@ class Context:
         """Column-block size for objectives with large random gathers (0 disables blocking)."""
         check(lib().cgo_ctx_set_gather_block_bytes(self.h, int(nbytes)))
 
+    def trim_pools(self) -> int:
+        """Give the pooled device blocks (vectors of closed workspaces) and the pooled pinned host buffers back;
+        returns the device bytes freed."""
+        v = C.c_int64()
+        check(lib().cgo_ctx_trim_pools(self.h, C.byref(v)))
+        capi.pinned_pool_clear()
+        return v.value
+
     def set_csr_mode(self, mode: int):
         """SpMV kernel family of CSR objectives created afterwards: 0 per matrix, 1 fused k_csr_rows, 2 k_spmv_direct."""
         check(lib().cgo_ctx_set_csr_mode(self.h, int(mode)))
@@ -215,6 +223,47 @@ def RosenbrockGPU(n: int, ctx: Optional[Context] = None) -> DeviceObjective:
     h = C.c_void_p()
     check(lib().cgo_obj_rosenbrock_create(ctx.h, n, C.byref(h)))
     return DeviceObjective(ctx, h)
+
+
+class _DevArray:
+    """a device pointer behind __cuda_array_interface__ (what torch.as_tensor wraps without a copy)"""
+
+    def __init__(self, ptr: int, n: int, readonly: bool):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, readonly), "version": 2}
+
+
+class UserObjectiveGPU(DeviceObjective):
+    """Any `fdf!(g, x) -> f` (src/engine/optim.jl:6-11) on the device: `fdf(g, x)` receives the gradient buffer and
+    the trial point as torch.float64 CUDA tensors (views of the solver's own vectors — this rank's shard), fills `g`
+    in place and returns f (a 0-dim CUDA tensor, or this rank's part of it when sharded).  It runs on the ctx stream
+    (torch.cuda.stream is set around the call) and must not synchronise.  The reference's signature and order of
+    arguments; the line search, β and the dots stay the library's (two BLAS-1 kernels per trial around the callback)."""
+
+    def __init__(self, n: int, fdf, ctx: Optional[Context] = None):
+        import torch
+        ctx = ctx or default_context()
+        self._torch, self._fdf = torch, fdf
+        self._stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", ctx.device))
+        self.last_error = None
+
+        def trampoline(_user, _stream, n_local, offset, xp, g, f):
+            try:
+                dev = torch.device("cuda", ctx.device)
+                with torch.cuda.stream(self._stream):
+                    x_t = torch.as_tensor(_DevArray(xp, n_local, True), device=dev)
+                    g_t = torch.as_tensor(_DevArray(g, n_local, False), device=dev)
+                    f_t = torch.as_tensor(_DevArray(f, 1, False), device=dev)
+                    val = fdf(g_t, x_t)
+                    f_t.copy_(torch.as_tensor(val, dtype=torch.float64, device=dev).reshape(1))
+                return 0
+            except Exception as e:      # an exception must not cross the C ABI
+                self.last_error = e
+                return 1
+
+        self._cb = capi.USER_FDF(trampoline)          # keep the thunk alive as long as the objective
+        h = C.c_void_p()
+        check(lib().cgo_obj_user_create(ctx.h, n, self._cb, None, C.byref(h)))
+        super().__init__(ctx, h)
 
 
 def RosenbrockChainedGPU(n: int, ctx: Optional[Context] = None) -> DeviceObjective:

@@ -48,8 +48,9 @@ class MinimizerRun:
                  fuse_direction: bool = True, beta_form: str = "fused", quadratic_linesearch: bool = False):
         if not hasattr(fdf_, "make_workspace"):
             raise TypeError(
-                "fdf! must be a device objective handle (RosenbrockGPU, SparseLSGPU, LogRegGPU, ...): "
-                "host callbacks cannot run on the GPU and this package has no CPU fallback")
+                "fdf! must be a device objective handle (RosenbrockGPU, SparseLSGPU, LogRegGPU, ..., or "
+                "UserObjectiveGPU(n, fdf) for your own fdf!(g, x) written on CUDA tensors): host callbacks "
+                "cannot run on the GPU and this package has no CPU fallback")
         assert isinstance(config, CGConfig) and isinstance(linesearch_config, LineSearchConfig)
         # ## parse.                                                         optim.jl:14-17
         self.fdf_ = fdf_

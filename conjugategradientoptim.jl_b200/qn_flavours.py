@@ -36,3 +36,21 @@ def getβ_lbfgs(β_config: LBFGS, ws) -> LBFGSHistoryToken:
         else:
             ws.lbfgs_commit_pair(False)
     return LBFGSHistoryToken()
+
+
+@dataclass(frozen=True)
+class BroydenFamily(QNβConfig):
+    """The reference's quasi-Newton config (qn_flavours.jl:53-62), kept so that code written against it still runs.
+    Its update sets `s = B\\y` (:81), which makes `B_new − B` vanish identically (`Bs = y` ⇒ `−Bs Bsᵀ/sᵀBs + y yᵀ/sᵀy
+    = 0`, and v = 0): B stays the identity it starts as, and `u = B\\(−g)` (:13-19) is the steepest-descent
+    direction (verified numerically there to O(1e-16)).  The dense n×n matrix with its O(n³)
+    factorisation per iteration is therefore not built here: this flavour returns β = 0, i.e. u = −g, which is
+    what the reference computes.  Use LBFGS(m) for an actual quasi-Newton direction."""
+    θ: float = 0.0
+    N: int = 0
+
+
+def setupBroydenFamily(θ, N: int) -> BroydenFamily:
+    """qn_flavours.jl:64-69"""
+    assert 0.0 <= θ <= 1.0
+    return BroydenFamily(float(θ), int(N))

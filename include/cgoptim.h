@@ -101,6 +101,9 @@ int cgo_ctx_set_sweep_window(cgo_ctx *ctx, int tiles);
  * k_spmv_direct (environment CGO_CSR_MODE).  Changes the canonical order of the dots (cgo_obj_reduction_site),
  * not the row sums. */
 int cgo_ctx_set_csr_mode(cgo_ctx *ctx, int mode);
+/* the ctx keeps the vectors of destroyed states for the next state of the same size (cudaMalloc / cudaFree of GB-sized
+ * blocks cost milliseconds and synchronise the device): up to 24 GB.  This gives them back to the driver. */
+int cgo_ctx_trim_pools(cgo_ctx *ctx, int64_t *freed_bytes);
 int cgo_ctx_sm_count(cgo_ctx *ctx, int *sms);
 int cgo_ctx_kernel_launches(cgo_ctx *ctx, int64_t *count);  /* kernels launched so far */
 /* optional per-launch CUDA-event timing on the ctx stream, by kernel class:
@@ -126,6 +129,16 @@ int cgo_shard_range(int64_t n, int nranks, int rank, int64_t align, int64_t *lo,
 /* ---------------------------------------------------------------- objectives --------------
  * Device-resident replacements of the user callback fdf!(g, x) -> f (optim.jl:25,
  * cg_utils.jl:18).  With a communicator on the ctx the constructors build this rank's shard. */
+/* ANY objective: the device form of the reference's user callback fdf!(g, x) -> f.  `fdf` is called once per trial
+ * on the host thread that drives the ctx and must ENQUEUE on `cuda_stream` (a cudaStream_t, the ctx stream) the
+ * work that, from the trial point xp_dev[0..n_local) (this rank's shard, global offset `offset`), writes the
+ * gradient to g_dev[0..n_local) and this rank's part of f to *f_dev (one device double; the ranks' parts are added
+ * in rank order).  It returns 0, or non-zero to abort the trial (reported as an error of cgo_eval_trial).  It must
+ * not synchronise the stream.  Everything else of evalϕdϕ! / getβ (xp = x + a u, dϕ, ‖g⁺‖², the β dots) is the
+ * library's.  n_global even (pad an odd problem with one fixed coordinate). */
+typedef int (*cgo_user_fdf)(void *user, void *cuda_stream, int64_t n_local, int64_t offset,
+                            const double *xp_dev, double *g_dev, double *f_dev);
+int cgo_obj_user_create(cgo_ctx *ctx, int64_t n_global, cgo_user_fdf fdf, void *user, cgo_obj **out);
 /* extended Rosenbrock (pairs) f = Σ 100 (x_{2i} − x_{2i−1}²)² + (1 − x_{2i−1})², n_global even */
 int cgo_obj_rosenbrock_create(cgo_ctx *ctx, int64_t n_global, cgo_obj **out);
 /* the reference's own chained Rosenbrock, rosenbrockfunc of examples/helpers/test_funcs.jl:50-57 with its

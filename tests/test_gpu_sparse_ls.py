@@ -330,6 +330,29 @@ def test_quadratic_aware_linesearch_matches_plain_path(ctx, flavour, linesearch)
     obj.close()
 
 
+@pytest.mark.parametrize("coh", [0, 30])
+def test_quadratic_linesearch_survives_other_users_of_the_objective(ctx, coh):
+    """The residual the quadratic-aware line search starts from belongs to one state; a Hessian-vector product or a
+    second workspace on the same objective overwrites it.  The library notices and forms r = A x − b again."""
+    n = 30_000
+    obj = cg.SparseLSGPU(n, 10, 512, 24, coh, ctx)
+    rng = np.random.default_rng(11)
+    a = obj.make_workspace(rng.standard_normal(n), quadratic_linesearch=True)
+    a.reset_direction()
+    ref = a.eval_trial(1e-3)                      # (ϕ, dϕ) from r(x) left by the state's own first evaluation
+    b = obj.make_workspace(rng.standard_normal(n), fuse_direction=False)     # another state on the same objective …
+    b.reset_direction()
+    b.hessvec_dir()                               # … and a Hessian-vector product: r is gone
+    a.reset_direction()                           # a new line search of the first state
+    again = a.eval_trial(1e-3)
+    assert again == ref
+    a.norm_df_xp()                                # materialise the step: r += a v, g⁺ = Aᵀ r
+    b.close()
+    fresh = obj.make_workspace(a.download_vector("xp"), fuse_direction=False)
+    assert abs(fresh.f_x0 - a.pack[0]) <= 1e-12 * fresh.f_x0
+    a.close(); fresh.close(); obj.close()
+
+
 def test_quadratic_aware_linesearch_rejects_what_it_cannot_do(ctx):
     obj = cg.SparseLSGPU(2000, 10, 64, 24, 0, ctx)
     _, cfg, ls = make_pair("HagerZhang", "Backtracking")
