@@ -447,7 +447,9 @@ def roofline_of(args, obj, m, n, coh, world, n_local, nnz_local):
             "whole_iteration_GBs_per_gpu": round(total_bytes / (ms * 1e-3) / 1e9, 1),
             "whole_iteration_frac": round(total_bytes / (ms * 1e-3) / 1e9 / peak, 4),
             "kernel_share_of_step": round((dom_ms / max(dom_cnt, 1)) * dom_per_eval * evals / ms, 4),
-            "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}}
+            "timers_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]},
+            "timers_launches": {k: round(v[1], 1) for k, v in timers.items() if v[1]},
+            "fdf_evals_per_s": round(evals / (ms * 1e-3), 2)}
 
 
 def run_ours(args):

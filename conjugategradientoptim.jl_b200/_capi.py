@@ -46,7 +46,6 @@ _SIGS = {
     "cgo_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "cgo_ctx_set_reduction_ctas": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_set_gather_block_bytes": (C.c_int, [_vp, C.c_int64]),
-    "cgo_ctx_set_sweep_window": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_set_csr_mode": (C.c_int, [_vp, C.c_int]),
     "cgo_ctx_trim_pools": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cgo_ctx_sm_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -88,7 +88,6 @@ extern "C" int cgo_ctx_create(int device, void *cuda_stream, cgo_ctx **out) {
     if (const char *e = getenv("CGO_CSR_PASS_OCC")) c->csr_pass_occ = (e[0] == '3') ? 3 : 2;
     if (const char *e = getenv("CGO_CSR_MODE")) c->csr_mode = atoi(e);
     if (const char *e = getenv("CGO_DIRECT_CFG")) c->direct_cfg = atoi(e);
-    if (const char *e = getenv("CGO_SWEEP_WINDOW")) c->sweep_window = atoi(e) > 0 ? atoi(e) : 0;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -157,12 +156,6 @@ extern "C" int cgo_ctx_set_csr_mode(cgo_ctx *c, int mode) {
     CGO_CHECK(c != nullptr, "NULL ctx");
     CGO_CHECK(mode >= 0 && mode <= 2, "cgo_ctx_set_csr_mode: mode %d out of [0,2]", mode);
     c->csr_mode = mode;
-    return 0;
-}
-extern "C" int cgo_ctx_set_sweep_window(cgo_ctx *c, int tiles) {
-    CGO_CHECK(c != nullptr, "NULL ctx");
-    CGO_CHECK(tiles >= 0, "cgo_ctx_set_sweep_window: negative window");
-    c->sweep_window = tiles;
     return 0;
 }
 extern "C" int cgo_ctx_kernel_launches(cgo_ctx *c, int64_t *count) {

@@ -59,17 +59,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
-// non-blocking: has the phase with this parity completed?
-__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -158,15 +147,9 @@ __device__ __forceinline__ double ld_gather_f64_if(const double *p, uint64_t pol
     return r;
 }
 
-// run-time knobs of the sweep
-struct TsKnobs {
-    int window;                        // lockstep window in tiles per CTA (0: free-running)
-    unsigned long long *progress;      // tiles consumed by all CTAs of this launch
-};
-
 // ---------------- producer: one lane streams tiles into the ring, about three tiles ahead
 template <class L, class Epi>
-__device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, const RedArgs &red, const TsKnobs &kn,
+__device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, const RedArgs &red,
                                            double *s_val, int32_t *s_col, unsigned char *s_desc, uint64_t *s_full,
                                            uint64_t *s_empty, uint32_t *s_len, int nact, int64_t ntiles) {
     constexpr int NOPS = Epi::NOPS;
@@ -180,32 +163,9 @@ __device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, cons
     bool have = true;
     int nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
     int64_t p0n = __ldg(A.rowptr + tile * CGO_B), p1n = __ldg(A.rowptr + tile * CGO_B + nvalid_n);
-    unsigned long long ktile = 0;     // own tiles issued so far
-    bool lockstep = kn.window > 0;
     while (have) {
         const int64_t r0 = tile * CGO_B, p0 = p0n, p1 = p1n;
         const int nvalid = nvalid_n;
-        // Lockstep window.  Every persistent CTA sweeps its own tiles v, v+G, v+2G, …; nothing else keeps the
-        // CTAs at the same height of the matrix, and on a 2e8-row matrix they drift apart by more rows than the
-        // band is wide: the window of the gathered vector that is live then exceeds L2 and every gather becomes
-        // a DRAM sector read (measured: 86 GB of DRAM reads against 30 GB algorithmic, 36 ms instead of 15).
-        // So a CTA never runs more than `window` tiles ahead of the grid's average progress.  Needs the grid to
-        // be co-resident (it is sized to be); if the count does not move for ~4 ms the CTA stops waiting.
-        if (lockstep && ktile >= (unsigned long long)kn.window) {
-            const unsigned long long need = (ktile - (unsigned long long)kn.window) * (unsigned long long)gridDim.x;
-            unsigned int polls = 0;
-            while (*(volatile unsigned long long *)kn.progress < need) {
-                // consumed chunks are only counted when they are reclaimed: reclaim what has been released
-                while (tail < c && mbar_test(&s_empty[tail % TS_ND], (tail / TS_ND) & 1)) {
-                    nfree += s_len[tail % TS_ND] & 0x7fffffffu;
-                    if (s_len[tail % TS_ND] >> 31) atomicAdd(kn.progress, 1ULL);
-                    ++tail;
-                }
-                __nanosleep(64);
-                if (++polls > (1u << 16)) { lockstep = false; break; }
-            }
-        }
-        ++ktile;
         have = ts_next_tile(v, tile, nact, ntiles, red.G);
         if (have) {                   // row pointers of the next tile: in flight during this one
             nvalid_n = (int)(nrows - tile * CGO_B < CGO_B ? nrows - tile * CGO_B : CGO_B);
@@ -219,12 +179,11 @@ __device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, cons
             // a free descriptor and cnt4 free ring entries: reclaim released chunks, oldest first
             while (tail + TS_ND <= c || nfree < cnt4) {
                 mbar_wait(&s_empty[tail % TS_ND], (tail / TS_ND) & 1);
-                nfree += s_len[tail % TS_ND] & 0x7fffffffu;
-                if (lockstep && (s_len[tail % TS_ND] >> 31)) atomicAdd(kn.progress, 1ULL);
+                nfree += s_len[tail % TS_ND];
                 ++tail;
             }
             const int d = c % TS_ND;
-            s_len[d] = cnt4 | (cs + CHMAX >= p1 ? 0x80000000u : 0u);       // bit 31: last chunk of its tile
+            s_len[d] = cnt4;
             nfree -= cnt4;
             unsigned char *desc = s_desc + d * L::DESC_BYTES;
             const uint32_t rpb = first ? (uint32_t)((((nvalid + 1) * 8) + 15) & ~15) : 0u;
@@ -255,7 +214,7 @@ __device__ __forceinline__ void ts_produce(const CsrMat &A, const Epi &epi, cons
 
 template <class Epi, int OCC>
 __global__ void __launch_bounds__(TS_THREADS, OCC)
-k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red, TsKnobs kn) {
+k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red) {
     constexpr int K = Epi::K;
     constexpr int NOPS = Epi::NOPS;
     using L = TsLayout<NOPS, OCC>;
@@ -280,7 +239,7 @@ k_csr_rows(CsrMat A, const double *__restrict__ xg, Epi epi, RedArgs red, TsKnob
 
     if (tid >= CGO_B) {                       // ---------------- producer warp
         if (tid == CGO_B && (int)blockIdx.x < nact)
-            ts_produce<L, Epi>(A, epi, red, kn, s_val, s_col, s_desc, s_full, s_empty, s_len, nact, ntiles);
+            ts_produce<L, Epi>(A, epi, red, s_val, s_col, s_desc, s_full, s_empty, s_len, nact, ntiles);
         return;
     }
 
@@ -364,11 +323,8 @@ static int launch_csr_occ(cgo_ctx *c, const CsrMat &A, const double *xg, const E
     CGO_CHECK(!A.sliced, "internal: k_csr_rows on a matrix in the sliced layout");
     const size_t smem = TsLayout<Epi::NOPS, OCC>::BYTES;
     CGO_CUDA(cudaFuncSetAttribute(k_csr_rows<Epi, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // the lockstep window only matters (and only costs a memset) when a CTA sweeps many tiles
-    TsKnobs kn{ntiles > 8 * (int64_t)grid ? c->sweep_window : 0, c->d_progress};
-    if (kn.window > 0) CGO_CUDA(cudaMemsetAsync(c->d_progress, 0, sizeof(unsigned long long), c->stream));
     cgo_timer_begin(c, tclass);
-    k_csr_rows<Epi, OCC><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red, kn);
+    k_csr_rows<Epi, OCC><<<grid, TS_THREADS, smem, c->stream>>>(A, xg, epi, red);
     cgo_timer_end(c);
     c->launches++;
     CGO_CUDA(cudaGetLastError());
@@ -570,8 +526,10 @@ static WithInit<Base> with_init(const Base &b, const double *partial) {
 //   k_spmv_direct  y = A x [− b | /N + λw | + partial]: no reduction ⇒ no canonical order to respect ⇒ any
 //                  grid, any schedule; 24-32 warps per SM, values and column indices read straight from HBM by
 //                  coalesced loads (sliced layout: the k-th entries of a slice's 32 rows are consecutive), no
-//                  shared memory, tiles handed out dynamically — which also keeps all warps inside one band
-//                  of the gathered vector, so it stays L2-resident (k_csr_rows needs a lockstep window for that);
+//                  shared memory, slices handed out dynamically — which also keeps all warps inside one band
+//                  of the gathered vector, so it stays L2-resident (the static tile order of k_csr_rows lets its
+//                  CTAs drift apart by more rows than the band is wide on a 2e8-row matrix: then every gather is
+//                  a DRAM sector read, 86 GB of DRAM traffic against 30 GB algorithmic, 36 ms instead of 15);
 //   k_blas1        the dots, in the BLAS-1 canonical order (V = 2, U = 4): Σ r² after K_b, the eight getβ dots
 //                  after K_c — 16n more bytes per evaluation than the fused epilogues (+5 %).
 // Each row's products are still added one by one in storage order: row sums are bit-identical to k_csr_rows'.

@@ -74,11 +74,9 @@ struct cgo_ctx {
     size_t gather_block_bytes = (size_t)40 << 20;   // column-block size of large random gathers (csr.cu)
     int csr_pass_occ = 2;                           // CTAs per SM of the column-block passes (CGO_CSR_PASS_OCC=3 to try 3)
     int64_t launches = 0;
-    // lockstep window of the CSR sweep in tiles per CTA (csr.cu ts_produce; 0: free-running)
-    int sweep_window = 8;
     int csr_mode = 0;        // 0: per matrix (sliced layout + k_spmv_direct when its gathers do not coalesce); 1: never; 2: always (CGO_CSR_MODE)
     int direct_cfg = 0;      // k_spmv_direct variant (CGO_DIRECT_CFG: 0 = 10 gathers per batch, 1 = 8; 4 CTAs per SM)
-    unsigned long long *d_progress = nullptr;   // [0] tiles consumed by all CTAs of the running k_csr_rows launch; [1..3] set-up scratch; [4] k_spmv_direct's slice queue
+    unsigned long long *d_progress = nullptr;   // [1..3] set-up scratch; [4] k_spmv_direct's slice queue
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax
     unsigned int *d_ticket = nullptr;

@@ -53,10 +53,6 @@ class Context:
         """SpMV kernel family of CSR objectives created afterwards: 0 per matrix, 1 fused k_csr_rows, 2 k_spmv_direct."""
         check(lib().cgo_ctx_set_csr_mode(self.h, int(mode)))
 
-    def set_sweep_window(self, tiles: int):
-        """Lockstep window of the CSR sweep in tiles per CTA (0: free-running); results do not depend on it."""
-        check(lib().cgo_ctx_set_sweep_window(self.h, int(tiles)))
-
     @property
     def stream_ptr(self) -> int:
         s = C.c_void_p()
@@ -229,7 +225,7 @@ class _DevArray:
     """a device pointer behind __cuda_array_interface__ (what torch.as_tensor wraps without a copy)"""
 
     def __init__(self, ptr: int, n: int, readonly: bool):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, readonly), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}   # (torch rejects the read-only flag)
 
 
 class UserObjectiveGPU(DeviceObjective):

@@ -92,10 +92,6 @@ int cgo_ctx_set_reduction_ctas(cgo_ctx *ctx, int G);        /* canonical-order G
  * evaluated one block per pass, so that the gathered window stays L2-resident (default 40 MiB;
  * 0 = never block).  Applies to objectives created afterwards; results are bit-identical. */
 int cgo_ctx_set_gather_block_bytes(cgo_ctx *ctx, int64_t bytes);
-/* lockstep window of the CSR sweep: a persistent CTA of the SpMV kernels never runs more than `tiles` of its
- * own 256-row tiles ahead of the grid's average progress, so that all CTAs gather from the same L2-resident
- * band of the vector (default 8; 0 = free-running; environment CGO_SWEEP_WINDOW).  Results do not depend on it. */
-int cgo_ctx_set_sweep_window(cgo_ctx *ctx, int tiles);
 /* which SpMV kernel family CSR objectives created afterwards use: 0 = per matrix (default: k_spmv_direct + BLAS-1
  * dots when its gathers do not coalesce, the fused k_csr_rows otherwise), 1 = always k_csr_rows, 2 = always
  * k_spmv_direct (environment CGO_CSR_MODE).  Changes the canonical order of the dots (cgo_obj_reduction_site),

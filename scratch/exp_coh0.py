@@ -16,7 +16,6 @@ ws.reset_direction()
 M = 12.0 * 10 * n + 8.0 * (n + 1)
 print(json.dumps({"n": n, "coh": coh}), flush=True)
 for w in windows:
-    ctx.set_sweep_window(w)
     ws.eval_trial(1e-3)      # warm
     ctx.timing(True); ctx.timing_read(reset=True)
     for i in range(3):
