@@ -22,7 +22,8 @@ import ConjugateGradientOptim: CGConfig, Results, TraceContainer, EnableTrace, D
     minimizeobjective, minimizeobjectivererun, linesearch!, evalϕdϕ!, getβ, updatedir!,
     initializeβ, initializeLineSearchContainer!, evalwolfeconditions, evalbacktrackcondition
 
-export Context, RosenbrockGPU, SparseLSGPU, LogRegGPU, LBFGS, DeviceObjective,
+export Context, RosenbrockGPU, RosenbrockChainedGPU, UserObjectiveGPU, SparseLSGPU, LogRegGPU, LBFGS, DeviceObjective,
+    DeviceStart, trial_site, set_csr_mode!, trim_pools!,
     BoxConstraint, BoxBarrierGPU, BatchedConfig, minimizeobjective_batched
 
 include("capi.jl")

@@ -50,6 +50,49 @@ function RosenbrockGPU(n::Integer, ctx::Context)
     check(ccall((:cgo_obj_rosenbrock_create, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, n, h))
     return _wrap(ctx, h[])
 end
+"The reference's own chained Rosenbrock, rosenbrockfunc (examples/helpers/test_funcs.jl:50-57), with its gradient."
+function RosenbrockChainedGPU(n::Integer, ctx::Context)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cgo_obj_rosenbrock_chained_create, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, n, h))
+    return _wrap(ctx, h[])
+end
+"""
+ANY `fdf!(g, x) -> f` on the device (include/cgoptim.h cgo_obj_user_create).  `fdf_dev(stream, n_local, offset, xp, g, f)`
+receives raw device pointers (`Ptr{Float64}`; wrap them with `unsafe_wrap(CuArray, …)` under CUDA.jl, or launch your
+own kernels) and must enqueue on `stream` the work that fills `g` with ∇f(xp) and `f[1]` with this rank's part of f.
+It returns nothing; an exception is reported as a failed trial, never thrown across the C ABI.
+"""
+function UserObjectiveGPU(n::Integer, fdf_dev, ctx::Context)
+    function thunk(user::Ptr{Cvoid}, stream::Ptr{Cvoid}, n_local::Int64, offset::Int64,
+                   xp::Ptr{Float64}, g::Ptr{Float64}, f::Ptr{Float64})::Cint
+        try
+            fdf_dev(stream, n_local, offset, xp, g, f)
+            return Cint(0)
+        catch
+            return Cint(1)
+        end
+    end
+    cb = @cfunction($thunk, Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cgo_obj_user_create, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                ctx.h, n, cb, C_NULL, h))
+    obj = _wrap(ctx, h[])
+    USER_THUNKS[obj.h] = cb          # keep the closure alive as long as the objective
+    return obj
+end
+const USER_THUNKS = Dict{Ptr{Cvoid},Any}()
+"(V, U) of the canonical reduction order the objective's trial dots follow (include/cgoptim.h)."
+function trial_site(obj::DeviceObjective)
+    v, u = Ref{Int32}(0), Ref{Int32}(0)
+    check(ccall((:cgo_obj_reduction_site, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}), obj.h, v, u))
+    return Int(v[]), Int(u[])
+end
+set_csr_mode!(ctx::Context, mode::Integer) = check(ccall((:cgo_ctx_set_csr_mode, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Cint), ctx.h, mode))
+function trim_pools!(ctx::Context)
+    freed = Ref{Int64}(0)
+    check(ccall((:cgo_ctx_trim_pools, LIBCGOPTIM[]), Cint, (Ptr{Cvoid}, Ref{Int64}), ctx.h, freed))
+    return freed[]
+end
 "½‖Ax − b‖², synthetic banded CSR (cfg 3), or from a host CSR (0-based int64 rowptr, int32 col)."
 function SparseLSGPU(n::Integer, ctx::Context; nnz_per_row = 10, W = min(1 << 20, (n - 1) ÷ 2), seed = 24, coh_log2 = 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -93,6 +136,22 @@ mutable struct DeviceWorkspace
     hint::Union{Nothing,Float64}
     cached::Union{Nothing,Tuple{Float64,Vector{Float64}}}
     β_literal::Bool
+end
+"`x_initial` that already lives on the device: the iterate of a live workspace (cgo_state_create_from_state)."
+struct DeviceStart
+    ws::Any
+end
+# the restart of minimizeobjectivererun (optim.jl:191-201) / a centering step (primal_barrier.jl:215-247) without H2D
+function DeviceWorkspace(obj::DeviceObjective, start::DeviceStart; lbfgs_m::Integer = 0, β_literal = false)
+    buf = zeros(PACK_LEN)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cgo_state_create_from_state, LIBCGOPTIM[]), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ref{Ptr{Cvoid}}, Ptr{Float64}),
+                obj.ctx.h, obj.h, start.ws.h, 0, lbfgs_m, h, buf))
+    ws = DeviceWorkspace(obj, h[], obj.n_local, buf, copy(buf), zeros(2), buf[P_PHI], sqrt(buf[P_GPGP]),
+                         nothing, nothing, nothing, β_literal)
+    finalizer(close!, ws)
+    return ws
 end
 # optim.jl:20-26: x = copy(x_initial); f_x = fdf!(df_x, x); norm(df_x)
 function DeviceWorkspace(obj::DeviceObjective, x_initial::Vector{Float64}; lbfgs_m::Integer = 0, β_literal = false)
