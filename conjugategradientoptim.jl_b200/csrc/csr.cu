@@ -709,9 +709,13 @@ static int launch_direct_k(cgo_ctx *c, const CsrMat &A, const double *xg, const 
 template <class F>
 static int launch_direct(cgo_ctx *c, const CsrMat &A, const double *xg, const F &f, const DirArgs &da, int tclass) {
     CGO_CHECK(A.sliced, "internal: k_spmv_direct needs the sliced layout");
-    // measured at n = 2e8, coh_log2 = 0 (K_b / K_c ms): 10 gathers per batch × 4 CTAs per SM 7.5 / 9.3;
-    // 8 × 4: 8.0 / 9.1; 5 × 4: 7.7 / 9.3; 10 × 3: 7.9 / 10.5; 8 × 3: 8.8 / 9.9
-    if (c->direct_cfg == 1) return launch_direct_k<F, 8, 4>(c, A, xg, f, da, tclass);
+    // gathers per batch × CTAs per SM, measured at n = 2e8, coh_log2 = 0 (K_b = ten entries in every row / K_c =
+    // ragged rows of Aᵀ, ms; profiles/r2_exp_coh0_n2e8_k_spmv_direct_configs.txt): 10 × 4: 7.5–7.9 / 9.3–10.5;
+    // 8 × 4: 8.0 / 9.1; 6 × 5: 7.7–8.1 / 9.1; 5 × 4: 7.7 / 9.3; 8 × 5 (spills): 8.4 / 9.5; 10 × 3: 7.9 / 10.5.
+    // Ragged slices waste the tail of a wide batch, equal-length rows like the widest batch that does not spill.
+    const int cfg = c->direct_cfg ? c->direct_cfg : (A.ragged ? 3 : 2);
+    if (cfg == 1) return launch_direct_k<F, 8, 4>(c, A, xg, f, da, tclass);
+    if (cfg == 3) return launch_direct_k<F, 6, 5>(c, A, xg, f, da, tclass);
     return launch_direct_k<F, 10, 4>(c, A, xg, f, da, tclass);
 }
 
@@ -957,10 +961,9 @@ static int csr_alloc(CsrMat &M, int64_t nrows, int64_t nnz) {
 // Re-order the entries of every 32-row slice level-major (CsrMat::sliced; k_csr_rows ts_issue).  Row pointers
 // stay CSR row pointers: a slice still owns the range [rowptr[32s], rowptr[32s+32)), only the order inside it
 // changes, and each row's own entries keep their relative order.
-// one warp per slice; inverse = back to row-major
-// one warp per slice; inverse = back to row-major
+// one warp per slice; inverse = back to row-major; *n_ragged (optional) += slices whose rows differ in length
 __global__ void k_slice_permute(CsrMat M, const int32_t *col_in, const double *val_in, int32_t *col_out, double *val_out,
-                                bool inverse) {
+                                bool inverse, unsigned long long *n_ragged = nullptr) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int64_t nslices = (M.nrows + 31) / 32;
@@ -970,6 +973,11 @@ __global__ void k_slice_permute(CsrMat M, const int32_t *col_in, const double *v
         int64_t rs = 0, len = 0;
         if (row < M.nrows) { rs = M.rowptr[row]; len = M.rowptr[row + 1] - rs; }
         const int64_t sb = M.rowptr[s * 32];
+        if (n_ragged != nullptr) {
+            const int64_t len0 = __shfl_sync(0xffffffffu, len, 0);
+            const bool same = __all_sync(0xffffffffu, row >= M.nrows || len == len0);
+            if (!same && lane == 0) atomicAdd(n_ragged, 1ULL);
+        }
         int64_t off = 0;
         for (int64_t k = 0;; ++k) {
             const uint32_t m = __ballot_sync(0xffffffffu, len > k);
@@ -1025,13 +1033,18 @@ static int csr_gather_lines(cgo_ctx *c, const CsrMat &M, float *lines) {
 static int csr_make_sliced(cgo_ctx *c, CsrMat &M) {
     if (M.sliced || M.nnz == 0 || !M.col || !M.val) return 0;
     int32_t *col2 = nullptr; double *val2 = nullptr;
+    unsigned long long n_ragged = 0;
     auto body = [&]() -> int {
         CGO_CUDA(cudaMalloc(&col2, sizeof(int32_t) * (size_t)(M.nnz + CSR_PAD)));
         CGO_CUDA(cudaMalloc(&val2, sizeof(double) * (size_t)(M.nnz + CSR_PAD)));
         CGO_CUDA(cudaMemsetAsync(col2 + M.nnz, 0, sizeof(int32_t) * CSR_PAD, c->stream));
         CGO_CUDA(cudaMemsetAsync(val2 + M.nnz, 0, sizeof(double) * CSR_PAD, c->stream));
-        k_slice_permute<<<grid_for((M.nrows + 31) / 32 * 32, c->sms), 256, 0, c->stream>>>(M, M.col, M.val, col2, val2, false);
+        unsigned long long *d_ragged = c->d_progress + 1;
+        CGO_CUDA(cudaMemsetAsync(d_ragged, 0, sizeof(unsigned long long), c->stream));
+        k_slice_permute<<<grid_for((M.nrows + 31) / 32 * 32, c->sms), 256, 0, c->stream>>>(M, M.col, M.val, col2, val2, false,
+                                                                                          d_ragged);
         CGO_CUDA(cudaGetLastError());
+        CGO_CUDA(cudaMemcpyAsync(&n_ragged, d_ragged, sizeof(n_ragged), cudaMemcpyDeviceToHost, c->stream));
         CGO_CUDA(cudaStreamSynchronize(c->stream));
         return 0;
     };
@@ -1040,6 +1053,7 @@ static int csr_make_sliced(cgo_ctx *c, CsrMat &M) {
     cudaFree(M.col); cudaFree(M.val);
     M.col = col2; M.val = val2;
     M.sliced = 1;
+    M.ragged = 16 * n_ragged > (unsigned long long)((M.nrows + 31) / 32);   // more than 1 slice in 16
     return 0;
 }
 

@@ -75,7 +75,7 @@ struct cgo_ctx {
     int csr_pass_occ = 2;                           // CTAs per SM of the column-block passes (CGO_CSR_PASS_OCC=3 to try 3)
     int64_t launches = 0;
     int csr_mode = 0;        // 0: per matrix (sliced layout + k_spmv_direct when its gathers do not coalesce); 1: never; 2: always (CGO_CSR_MODE)
-    int direct_cfg = 0;      // k_spmv_direct variant (CGO_DIRECT_CFG: 0 = 10 gathers per batch, 1 = 8; 4 CTAs per SM)
+    int direct_cfg = 0;      // k_spmv_direct variant (CGO_DIRECT_CFG: 0 = by matrix, 2 = 10 gathers per batch × 4 CTAs/SM, 1 = 8 × 4, 3 = 6 × 5)
     unsigned long long *d_progress = nullptr;   // [1..3] set-up scratch; [4] k_spmv_direct's slice queue
     // reduction scratch
     double *d_partial = nullptr;     // CGO_MAXK * Gmax
@@ -236,6 +236,7 @@ struct CsrMat {
     // sliced: inside every 32-row slice [rowptr[32s], rowptr[32s+32]) the entries are stored level-major
     // (all first entries of the slice's rows in row order, then all second entries, …) instead of row-major
     int32_t sliced = 0;
+    int32_t ragged = 0;          // sliced: more than one slice in 16 has rows of different lengths (picks the batch width)
     int64_t max_tile_nnz = 0;    // most entries in any 256-row tile
     float lines_per_gather = 1.f;   // distinct 128-byte lines one warp-level gather touches (sampled at set-up)
 };
