@@ -52,6 +52,7 @@ def parse():
                         "the headline; 30: the same offsets for all rows, i.e. ten true diagonals — reported as "
                         "`secondary` by the default run)")
     p.add_argument("--no-secondary", action="store_true", help="sparse_ls: skip the second matrix variant")
+    p.add_argument("--max-reps", type=int, default=100, help="cap on the repetitions of the K-step measurement")
     p.add_argument("--min-timed-s", type=float, default=2.0,
                    help="repeat the K-step measurement (fresh run from x0 each time) until the timed region is this long")
     p.add_argument("--write-fixture", action="store_true",
@@ -343,6 +344,7 @@ def measure_device(cg, torch, args, ctx, obj, x0, n, coh, world, rank, local_ran
     ctx.timing(True)
     ctx.timing_read(reset=True)
     first = True
+    t_loop = time.perf_counter()
     while True:
         run = cg.MinimizerRun(obj, x0, cfg, ls, **qkw)
         ctx.timing(False)
@@ -396,7 +398,13 @@ def measure_device(cg, torch, args, ctx, obj, x0, n, coh, world, rank, local_ran
             import torch.distributed as dist
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms_tot += float(tms.item())
-        if ms_tot * 1e-3 >= args.min_timed_s or reps >= 12:
+        # (the wall-clock guard is rank 0's and every rank applies rank 0's verdict through the reduced flag below)
+        stop = ms_tot * 1e-3 >= args.min_timed_s or reps >= args.max_reps or time.perf_counter() - t_loop > 90.0
+        tstop = torch.tensor([1.0 if stop else 0.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tstop, op=dist.ReduceOp.MAX)
+        if float(tstop.item()) > 0:
             break
     sampler.mark_end()
     barrier()
