@@ -664,10 +664,10 @@ def run_batched(args):
                 # gradient 12, y 2, six dots 25); no FMA anywhere (the reference's arithmetic is unfused), so the
                 # pipe's ceiling is one DADD/DMUL per FP64 lane and clock: 64 lanes x SMs x max SM clock
                 "roofline": {"bound": "fp64 pipe (on-chip: registers + shuffles; HBM roofline not applicable)",
-                             "achieved": round(tot_ev * K * (n / 2) * 43 / (kms * 1e-3) / 1e12, 3),
+                             "achieved": round(tot_ev * K * (n / 2) * 43 / (kms * 1e-3) / 1e12 / world, 3),   # per GPU, like the peak
                              "peak": round(64 * ctx.sm_count * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12, 3)
                              if clocks and clocks.get("sm_max_mhz") else round(64 * ctx.sm_count * 1965e6 / 1e12, 3),
-                             "unit": "TFLOP/s (unfused FP64 instructions)", "frac": None, "traffic": None,
+                             "unit": "TFLOP/s per GPU (unfused FP64 instructions)", "frac": None, "traffic": None,
                              "peak_source": "nominal: 64 FP64 lanes/SM/clk x SM count x max SM clock, FMA not usable"},
                 "e2e": {"value": round(tot_it * K / wall, 1), "unit": "iterations/s",
                         "h2d_bytes_per_step": 8.0 * nprob * n, "d2h_bytes_per_step": 8.0 * nprob * n + 36.0 * nprob,
