@@ -21,13 +21,13 @@ def _ngpus():
 
 def _evidence(world, no_peer):
     """the retained log of this very case from a box that had the GPUs (profiles/, written by
-    scratch/gpu_r2_multi_parity.sh / gpu_r2_multi8.sh)"""
+    scratch/gpu_r2_finalN.sh N)"""
     name = f"r2_multirank_parity_{world}gpu_{'nccl_exchange' if no_peer else 'peer_memory'}.log"
     path = os.path.join(ROOT, "profiles", name)
     return path, (open(path).read() if os.path.exists(path) else None)
 
 
-@pytest.mark.parametrize("world,no_peer", [(2, 0), (2, 1), (8, 0), (8, 1)])
+@pytest.mark.parametrize("world,no_peer", [(2, 0), (2, 1), (4, 0), (4, 1), (8, 0), (8, 1)])
 def test_sharded_runs_bit_exact(world, no_peer):
     """no_peer = 0: halo pushes over peer memory (CUDA IPC) fused into the kernels;
     no_peer = 1: the NCCL point-to-point exchange path.  Both must match the oracle bit for bit.
@@ -42,7 +42,7 @@ def test_sharded_runs_bit_exact(world, no_peer):
         if f"SOURCES_SHA={multirank_worker.sources_sha()}" not in log:
             import warnings
             warnings.warn(f"{os.path.basename(path)} was produced by other sources than the current tree: re-run "
-                          f"scratch/gpu_r2_multi_parity.sh on a {world}-GPU box")
+                          f"scratch/gpu_r2_finalN.sh {world} on a {world}-GPU box")
         pytest.skip(f"needs {world} GPUs; retained passing log checked: {os.path.basename(path)}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29511 + world + 10 * no_peer),
