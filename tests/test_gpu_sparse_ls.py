@@ -90,6 +90,64 @@ def test_from_csr_ragged_bit_exact(ctx, nrows, ncols, long_row):
     obj.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nrows,ncols,long_row", [(1, 1, None), (33, 40, 5), (257, 300, None), (5000, 3001, 17),
+                                                  (4100, 4100, 4099)])
+def test_from_csr_ragged_both_kernel_families(mode, nrows, ncols, long_row):
+    """The same ragged inputs with the kernel family forced (cgo_ctx_set_csr_mode: 1 = k_csr_rows, TMA ring, fused
+    dots; 2 = sliced layout + k_spmv_direct, dots in BLAS-1 passes): empty rows, a last slice of fewer than 32 rows,
+    a 7000-entry row (many batches of either width), slices of unequal lengths.  SpMV, SpMVᵀ, the downloaded
+    matrices, f, g and a short CG run must equal the oracle at the objective's own reduction site."""
+    c = cg.Context(0)
+    c.set_csr_mode(mode)
+    try:
+        rowptr, col, val, b = _ragged_csr(nrows, ncols, 5, long_row)
+        obj = cg.SparseLSGPU_from_csr(nrows, ncols, rowptr, col, val, b, c)
+        assert obj.trial_site == ((2, 4) if mode == 2 else (1, 1))
+        ora = O.Objective.sparse_ls_csr(nrows, ncols, rowptr, col, val, b)
+        ora.set_trial_site(*obj.trial_site)
+        ora.set_sum_mode("cgo")
+        rp, ci, va, bb = obj.csr(False)                   # a sliced matrix comes back row-major
+        assert np.array_equal(rp, rowptr) and np.array_equal(ci, col) and np.array_equal(va, val) and np.array_equal(bb, b)
+        rpT, ciT, vaT, _ = obj.csr(True)
+        orpT, ociT, ovaT = ora.csr(True)
+        assert np.array_equal(rpT, orpT) and np.array_equal(ciT, ociT) and np.array_equal(vaT, ovaT)
+        rng = np.random.default_rng(7)
+        x, y = rng.standard_normal(ncols), rng.standard_normal(nrows)
+        assert np.array_equal(obj.spmv(x), ora.spmv(x))
+        assert np.array_equal(obj.spmv(y, transposed=True), ora.spmv(y, transposed=True))
+        ws = obj.make_workspace(x, fuse_direction=False)
+        f, g = ora.fdf(x)
+        assert ws.f_x0 == f and np.array_equal(ws.download()[1], g)
+        ws.close()
+        if nrows > 1:
+            ocfg, cfg, ls = make_pair("HagerZhang", max_iters=8)
+            assert_same_run(cg.minimizeobjective(obj, np.zeros(ncols), cfg, ls), O.minimize(ora, np.zeros(ncols), ocfg))
+        obj.close()
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("mode,coh", [(1, 0), (2, 30), (2, 3)])
+def test_synthetic_matrix_on_the_other_kernel_family(mode, coh):
+    """The generator picks the kernel family from the coherence of the offsets; forcing the other one must change
+    nothing but the site of the Σr² reduction (which the oracle follows): whole runs stay bit-exact."""
+    c = cg.Context(0)
+    c.set_csr_mode(mode)
+    try:
+        n = 50_000
+        obj = cg.SparseLSGPU(n, 10, 4096, 24, coh, c)
+        assert obj.trial_site == ((2, 4) if mode == 2 else (1, 1))
+        ora = O.Objective.sparse_ls(n, 10, 4096, 24, coh)
+        ora.set_trial_site(*obj.trial_site)
+        for flavour in ("HagerZhang", "LBFGS"):
+            ocfg, cfg, ls = make_pair(flavour, max_iters=12)
+            assert_same_run(cg.minimizeobjective(obj, np.zeros(n), cfg, ls), O.minimize(ora, np.zeros(n), ocfg))
+        obj.close()
+    finally:
+        c.close()
+
+
 def test_from_csr_rejects_bad_input(ctx):
     rowptr, col, val, b = _ragged_csr(10, 10, 1)
     col2 = col.copy()
