@@ -55,6 +55,8 @@ def parse():
     p.add_argument("--max-reps", type=int, default=100, help="cap on the repetitions of the K-step measurement")
     p.add_argument("--min-timed-s", type=float, default=2.0,
                    help="repeat the K-step measurement (fresh run from x0 each time) until the timed region is this long")
+    p.add_argument("--no-parity-assert", action="store_true",
+                   help="report parity_vs_n1 of the headline variant without failing when it exceeds 1e-10")
     p.add_argument("--write-fixture", action="store_true",
                    help="N = 1: (re)write tests/golden/bench_trace_n1.json, the objective traces `parity_vs_n1` checks against")
     p.add_argument("--reduction-ctas", type=int, default=0, help="canonical-order G (0: library default)")
@@ -322,7 +324,20 @@ def parity_vs_n1(args, n, coh, trace):
     if k == 0:
         return None, "empty trace"
     rel = np.abs(np.asarray(trace[:k]) - ref[:k]) / np.abs(ref[:k])
-    return float(rel.max()), f"first {k} iterations"
+    bad = np.nonzero(rel > PARITY_TOL)[0]
+    within = int(bad[0]) if bad.size else k
+    return float(rel.max()), f"first {k} iterations; within {PARITY_TOL:g} over the first {within}"
+
+
+PARITY_TOL = 1e-10      # north_star's gate on per-iteration f (SURVEY.md §8d "Parity gates")
+
+
+def parity_gate(args, par, what):
+    """The headline variant must reproduce the committed one-GPU trace to PARITY_TOL at every rank count (its
+    reductions are deterministic for a fixed N, so this either always holds or never does)."""
+    if par is not None and par > PARITY_TOL and not args.no_parity_assert:
+        raise AssertionError(f"{what}: objective trace differs from the N = 1 fixture by {par:.3e} > {PARITY_TOL:g} "
+                             f"(--no-parity-assert reports it without failing)")
 
 
 def measure_device(cg, torch, args, ctx, obj, x0, n, coh, world, rank, local_rank, stream, barrier):
@@ -500,6 +515,8 @@ def run_ours(args):
     K, W, ms, qkw, life = m["K"], m["W"], m["ms"], m["qkw"], m["life"]
     roofline = roofline_of(args, obj, m, n, coh, world, n_local, nnz_local)
     par, par_note = parity_vs_n1(args, n, coh, m["trace"])
+    if rank == 0:
+        parity_gate(args, par, f"{args.workload} n={n} coh_log2={coh}")
 
     # ---------------- end-to-end through the public API (`e2e`) ----------------
     e2e = None
@@ -576,7 +593,7 @@ def run_ours(args):
                        if args.workload == "sparse_ls" else "the only variant"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(round(m["launches"])), "clocks": m["clocks"],
             "host_wall_ms_per_step": round(m["wall_ms"] / K, 4),
-            "parity_vs_n1": par, "parity_vs_n1_note": par_note,
+            "parity_vs_n1": par, "parity_vs_n1_note": par_note, "parity_tol": PARITY_TOL,
             "objective_trace_head": [float(v) for v in m["trace"][:4]],
             "secondary": secondary,
         }

@@ -78,7 +78,17 @@ def test_parity_fixture_lookup(bench, tmp_path, monkeypatch):
     tr = np.array([3.0, 2.0, 1.0])
     assert bench.parity_vs_n1(a, 1000, 0, tr)[0] is None                      # no fixture yet
     bench.write_fixture(a, 1000, 0, tr)
-    assert bench.parity_vs_n1(a, 1000, 0, tr) == (0.0, "first 3 iterations")
+    assert bench.parity_vs_n1(a, 1000, 0, tr) == (0.0, "first 3 iterations; within 1e-10 over the first 3")
     rel, _ = bench.parity_vs_n1(a, 1000, 0, tr * (1 + 1e-12))
     assert 0 < rel < 2e-12
     assert bench.parity_vs_n1(a, 1000, 30, tr)[0] is None                     # another configuration
+    rel, note = bench.parity_vs_n1(a, 1000, 0, tr * np.array([1.0, 1 + 1e-12, 1 + 1e-9]))
+    assert rel > bench.PARITY_TOL and note.endswith("over the first 2")
+    a.no_parity_assert = False
+    bench.parity_gate(a, 1e-11, "x")
+    bench.parity_gate(a, None, "x")
+    import pytest
+    with pytest.raises(AssertionError):
+        bench.parity_gate(a, rel, "x")
+    a.no_parity_assert = True
+    bench.parity_gate(a, rel, "x")
