@@ -248,7 +248,7 @@ def algorithmic_bytes(args, n_local, nnz_local, evals, iters):
 
 def ncu_traffic(args, world, n, coh=None):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very
-    configuration (profiles/, taken with the commands in scratch/profile_r1.sh, scratch/gpu_r2_call10.sh); None for
+    configuration (profiles/, taken with the commands in scratch/profile_r1.sh, scratch/gpu_r2_ncu_final.sh); None for
     any other configuration."""
     coh = args.coh if coh is None else coh
     name = {"sparse_ls": ("r1_ncu_full_ls_r1b.txt", 200_000_000), "rosenbrock": ("r1_ncu_full_rosen_r1.txt", 100_000_000)}
