@@ -52,6 +52,8 @@ def parse():
                         "the headline; 30: the same offsets for all rows, i.e. ten true diagonals — reported as "
                         "`secondary` by the default run)")
     p.add_argument("--no-secondary", action="store_true", help="sparse_ls: skip the second matrix variant")
+    p.add_argument("--gather-block-mib", type=float, default=0.0,
+                   help="logreg: size of the column blocks of the gathered vectors (0: library default, 40 MiB)")
     p.add_argument("--max-reps", type=int, default=100, help="cap on the repetitions of the K-step measurement")
     p.add_argument("--min-timed-s", type=float, default=2.0,
                    help="repeat the K-step measurement (fresh run from x0 each time) until the timed region is this long")
@@ -490,6 +492,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = cg.Context(local_rank)
+    if args.gather_block_mib > 0:
+        ctx.set_gather_block_bytes(int(args.gather_block_mib * (1 << 20)))
     if args.reduction_ctas:
         ctx.set_reduction_ctas(args.reduction_ctas)
     if world > 1:
