@@ -285,7 +285,7 @@ def test_large_n_properties(ctx, n):
 
 @pytest.mark.parametrize("coh", [0, 30])
 def test_oracle_compared_run_n2e7(ctx, coh):
-    """A run at a tenth of the full size (n = 2e7, 2e8 nonzeros: 264 tiles per persistent CTA, the lockstep window,
+    """A run at a tenth of the full size (n = 2e7, 2e8 nonzeros: 264 tiles per persistent CTA,
     the dynamic slice queue, multi-tile reductions) against the oracle in the canonical order, bit for bit: five
     iterations, both matrix variants (coh 0: k_spmv_direct + BLAS-1 dots; coh 30: fused k_csr_rows)."""
     n = 20_000_000
