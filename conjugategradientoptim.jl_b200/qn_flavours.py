@@ -1,8 +1,8 @@
 """Quasi-Newton direction plugin — the slot of src/qn_flavours.jl.
 
 The reference's `BroydenFamily` (qn_flavours.jl:53-90) keeps a dense n×n matrix, costs O(n³) per
-iteration and, because it sets `s = B\\y` (:81), is a mathematical no-op: it is
-out of scope.  `LBFGS(m)` is the new flavour behind the same four-method plugin interface
+iteration and, because it sets `s = B\\y` (:81), is a mathematical no-op: the matrix is
+not built; `BroydenFamily` below is kept as what that update computes.  `LBFGS(m)` is the new flavour behind the same four-method plugin interface
 (initializeβ, initializeLineSearchContainer!, getβ, updatedir!): textbook two-loop recursion
 (Nocedal & Wright Alg. 7.4/7.5) over the m stored (s, y) pairs, s = xp − x, y = g⁺ − g,
 H₀ = (s·y / y·y) I, pair kept only when s·y > 0.
@@ -51,6 +51,6 @@ class BroydenFamily(QNβConfig):
 
 
 def setupBroydenFamily(θ, N: int) -> BroydenFamily:
-    """qn_flavours.jl:64-69"""
-    assert 0.0 <= θ <= 1.0
+    """qn_flavours.jl:55-62 (only the lower bound on θ is asserted there: `@assert zero(T) <= θ #<= one(T)`)"""
+    assert 0.0 <= θ
     return BroydenFamily(float(θ), int(N))

@@ -199,3 +199,27 @@ def test_large_n_properties(ctx):
     f1, _ = O.Objective.rosenbrock(2).fdf(xp)
     assert abs(ret.objective - f1 * (n // 2)) <= 1e-12 * abs(ret.objective)
     assert ret.iters_ran == 8 and np.all(np.diff(ret.trace.objective) < 0)
+
+
+def test_trim_pools_gives_the_retained_blocks_back():
+    """cgo_ctx_trim_pools: the device blocks a closed workspace left in the ctx pool (and the pooled pinned host
+    buffers) are freed on request; the ctx keeps working afterwards and the next run reproduces the previous one."""
+    import torch
+    c = cg.Context(0)
+    try:
+        n = 4_000_000
+        obj = cg.RosenbrockGPU(n, c)
+        _, cfg, ls = make_pair("HagerZhang", max_iters=5)
+        x0 = obj.default_x0(24, 0.1)
+        a = cg.minimizeobjective(obj, x0, cfg, ls)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        freed = c.trim_pools()
+        assert freed >= 5 * 8 * n                       # x, g, u, xp, g⁺ of the closed workspace
+        assert torch.cuda.mem_get_info()[0] >= free0 + 5 * 8 * n - (64 << 20)
+        assert c.trim_pools() == 0                      # nothing left to give back
+        b = cg.minimizeobjective(obj, x0, cfg, ls)
+        assert np.array_equal(a.trace.objective, b.trace.objective) and np.array_equal(a.minimizer, b.minimizer)
+        obj.close()
+    finally:
+        c.close()

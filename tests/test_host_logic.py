@@ -97,3 +97,39 @@ def test_disable_trace():
     x0 = np.array([0.43, 1.23])
     ret = cg.minimizeobjective(NumpyObjective(O.Objective.booth()), x0, cfg, ls)
     assert ret.status == "success" and len(ret.trace.objective) == 0
+
+
+def test_broyden_family_is_what_the_reference_computes():
+    """src/qn_flavours.jl:72-90 restated with the dense matrix: with `s = B\\y` the update leaves B where it is
+    (B starts as the identity, :31-34), so `u = B\\(-df_x)` (:17) is −df_x — which is what the kept
+    `BroydenFamily` flavour does without the n×n matrix (β = 0)."""
+    rng = np.random.default_rng(5)
+    n = 12
+    for θ in (0.0, 0.3, 1.0, 2.5):
+        B = np.eye(n)
+        for _ in range(20):                                   # getβ, qn_flavours.jl:78-88
+            g, g_next = rng.standard_normal(n), rng.standard_normal(n)
+            y = g_next - g
+            s = np.linalg.solve(B, y)
+            Bs = B @ s
+            sBs = s @ Bs
+            v = y / (s @ y) - Bs / sBs
+            B = B - np.outer(Bs, Bs) / sBs + np.outer(y, y) / (s @ y) + θ * sBs * np.outer(v, v)
+            assert np.abs(B - np.eye(n)).max() < 1e-12
+            assert np.allclose(np.linalg.solve(B, -g_next), -g_next, rtol=0, atol=1e-11)   # updatedir!, :17
+    cfgθ = cg.setupBroydenFamily(2.5, 2)                      # only `0 <= θ` is asserted (:57)
+    with pytest.raises(AssertionError):
+        cg.setupBroydenFamily(-0.1, 2)
+    # the flavour itself: every direction is −df_x, i.e. the run equals a CG run whose β is always 0
+    from cgoptim_b200 import cg_flavours
+    x0 = np.array([0.43, 1.23])
+    _, _, ls = make_pair("HagerZhang")
+    cfg = cg.setupCGConfig(1e-5, cfgθ, cg.EnableTrace(), max_iters=400)
+    run = cg.MinimizerRun(NumpyObjective(O.Objective.booth()), x0, cfg, ls)
+    for _ in range(5):
+        assert run.step() is None
+        assert run.β == 0.0 or float(run.β) == 0.0
+        run.info.dot_g_u()                                   # materialises the deferred updatedir!
+        assert np.array_equal(run.info.u_, -run.info.g_)
+    ret = cg.minimizeobjective(NumpyObjective(O.Objective.booth()), x0, cfg, ls)
+    assert ret.status == "success" and np.allclose(ret.minimizer, [1.0, 3.0], atol=1e-4)
