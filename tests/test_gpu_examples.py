@@ -1,0 +1,53 @@
+"""The reference's two example scripts, restated on the device API (examples/min.py, examples/constrained.py), run
+as a user would run them and checked against the reference's own known answers — Booth's minimiser [1, 3] with
+f* = 0 (test/runtests.jl:17-21; examples/constrained.jl:162 prints it as the global minimum) — and against the
+oracle driven with the same configurations."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cgoptim_b200 as cg  # noqa: F401
+from oracle import oracle as O
+
+from helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+
+
+def test_example_min():
+    import min as example
+    ret, big = example.main(verbose=False, n_large=1_000_000)
+    assert ret.status == "success" and np.allclose(ret.minimizer, [1.0, 3.0], atol=1e-5)
+    assert ret.objective < 1e-9 and np.linalg.norm(ret.gradient) < 1e-5
+    ora = O.minimize(O.Objective.booth(), np.array([0.43, 1.23]), make_pair("HagerZhang")[0])
+    assert ret.iters_ran == ora.iters_ran and np.array_equal(ret.trace.step_size, ora.trace_step_size)
+    assert np.array_equal(ret.trace.objective_evals, ora.trace_objective_evals)
+    assert big.status == "success" and np.abs(big.minimizer - 1.0).max() < 1e-4      # test_funcs.jl:48
+
+
+def test_example_constrained():
+    """The barrier method walks the central path towards Booth's minimiser (the box is inactive there): each
+    centering step that succeeds lands ≈10× closer (‖x*(t) − x*‖ ∝ 1/t, t grows by 10).  With the example's ϵ = 1e-5 on
+    the gradient of t·f0 + ψ the line searches give up once t reaches 1e5…1e8 — the oracle's restatement stops the
+    same way (`:centering_step_issue`, primal_barrier.jl:224-232) — so the outcome asserted is the path, not the
+    final status, which no reference output pins."""
+    import constrained as example
+    b = example.main(verbose=False)
+    assert b.status in ("success", "centering_step_issue") and b.iters_ran >= 4
+    x_star = np.array([1.0, 3.0])
+    dist = [np.linalg.norm(step[-1].minimizer - x_star) for step in b.centering_results]
+    assert all(step[-1].status == "success" for step in b.centering_results[:3])
+    assert dist[0] < 1e-4 and dist[1] < 0.2 * dist[0] and dist[2] < 0.2 * dist[1] and dist[-1] < 1e-6
+    assert all(np.all(np.abs(r.minimizer) < 10.0) for step in b.centering_results for r in step)
+    assert all(r.h2d_bytes == 0 for step in b.centering_results for r in step)       # device-resident restarts
+    # the oracle's restatement of the method on the first centering steps (primary pair only succeeds there)
+    o1 = make_pair("HagerZhang", "Wolfe", c1=1e-3, c2=0.9, ls_max_iters=100, eps=1e-5)[0]
+    ob = O.primalbarrier(O.Objective.booth(), -10.0 * np.ones(2), 10.0 * np.ones(2), np.array([0.43, 1.23]), [o1],
+                         1e-8, 10.0, 3)
+    assert b.centering_results[0][0].h2d_bytes == 0
+    for step, ostep in zip(b.centering_results[:3], ob.centering_results):
+        assert len(step) == 1 and abs(step[0].iters_ran - ostep[0].iters_ran) <= 2
+        np.testing.assert_allclose(step[0].minimizer, ostep[0].minimizer, atol=1e-8)
