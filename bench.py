@@ -529,34 +529,49 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         x0p = torch.from_numpy(x0.copy()).pin_memory().numpy()
-        # one untimed call first: page-locks the result buffers (they are pooled and reused) and
-        # warms the allocator, as a long-running host would have done
-        cfg1, ls1 = solver_configs(cg, 1, args.workload)
-        cg.minimizeobjective(obj, x0p, cfg1, ls1, **qkw)
-        remaining, dt, ev2, calls = K, 0.0, 0, 0
-        while remaining > 0:                                 # more than one call only if a run hits the FP64 floor
-            per_call = remaining if life is None else max(1, min(remaining, life - 3))
-            cfg2, ls2 = solver_configs(cg, per_call, args.workload)
-            barrier()
-            t0 = time.perf_counter()
-            ret = cg.minimizeobjective(obj, x0p, cfg2, ls2, **qkw)  # H2D x0 … iterations … D2H x, g
-            barrier()
-            dt += time.perf_counter() - t0
-            assert ret.iters_ran > 0, (ret.iters_ran, ret.status)
-            remaining -= ret.iters_ran
-            ev2 += int(ret.trace.objective_evals.sum())
-            calls += 1
-        tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-        dt = float(tdt.item())
+
+        def public_call(kw):
+            """K iterations through `minimizeobjective` with host vectors -> (seconds, max over ranks; evals; calls)"""
+            # one untimed call first: page-locks the result buffers (they are pooled and reused) and
+            # warms the allocator, as a long-running host would have done
+            cfg1, ls1 = solver_configs(cg, 1, args.workload)
+            cg.minimizeobjective(obj, x0p, cfg1, ls1, **kw)
+            remaining, dt, ev2, calls = K, 0.0, 0, 0
+            while remaining > 0:                                 # more than one call only if a run hits the FP64 floor
+                per_call = remaining if life is None else max(1, min(remaining, life - 3))
+                cfg2, ls2 = solver_configs(cg, per_call, args.workload)
+                barrier()
+                t0 = time.perf_counter()
+                ret = cg.minimizeobjective(obj, x0p, cfg2, ls2, **kw)  # H2D x0 … iterations … D2H x, g
+                barrier()
+                dt += time.perf_counter() - t0
+                assert ret.iters_ran > 0, (ret.iters_ran, ret.status)
+                remaining -= ret.iters_ran
+                ev2 += int(ret.trace.objective_evals.sum())
+                calls += 1
+            tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            return float(tdt.item()), ev2, calls
+
+        dt, ev2, calls = public_call(qkw)
         e2e = {"value": round(K / dt, 4), "unit": "iterations/s",
                "h2d_bytes_per_step": round((8.0 * n_local * calls + 16.0 * (ev2 + K)) / K, 1),
                "d2h_bytes_per_step": round((16.0 * n_local * calls + 128.0 * (ev2 + 2 * K)) / K, 1),
                "api_calls": calls,
                "includes": "x0 H2D from pinned host memory, f/g at x0, K iterations (scalar pack D2H "
                            "every launch), minimizer+gradient D2H", "wall_s": round(dt, 4)}
+        if args.workload == "sparse_ls" and not qkw:
+            # the same call with the quadratic-aware line search (SURVEY.md §8f N1: one SpMV + one SpMVᵀ per iteration
+            # whatever the number of trials — the first line search of a run takes five): reported beside the
+            # headline, which stays the plain path
+            try:            # (line-search scalars are replicated, so every rank takes the same branch here)
+                dtq, evq, callsq = public_call({"quadratic_linesearch": True})
+                e2e["quadratic_aware_linesearch"] = {"value": round(K / dtq, 4), "unit": "iterations/s",
+                                                     "api_calls": callsq, "fdf_evals": evq, "wall_s": round(dtq, 4)}
+            except AssertionError as e:
+                e2e["quadratic_aware_linesearch"] = {"error": str(e)[:200]}
 
     # ---------------- the other matrix variant of cfg 3, same run (`secondary`) ----------------
     secondary = None
