@@ -8,7 +8,9 @@ The reference's `hdh!` fills 2n dense constraint gradients (examples/constrained
 Outcome on a B200: three centering steps succeed, each ≈10× closer to Booth's minimiser [1, 3] (the box is inactive
 there); from t ≈ 2.5e5 on the example's ϵ = 1e-5 is below what its line searches resolve on t·f0 + ψ and the method
 returns `centering_step_issue` at ‖x − [1, 3]‖ ≈ 6e-8 — the oracle's restatement of the reference stops the same way
-a few steps later; what the Julia package prints is not recorded anywhere in the reference.
+a few steps later.  The reference's README.md:10 says as much about its own barrier method ("successively solves
+harder and harder unconstrained optimization problems, to the point that linesearch failures are common due to finite
+numerical precision"); what the Julia package prints for this script is not recorded anywhere in the reference.
 
     python examples/constrained.py      (needs a B200; there is no CPU fallback)
 """
