@@ -31,6 +31,7 @@ SYM(int, cgo_ctx_create, (int, void *, cgo_ctx **));
 SYM(int, cgo_ctx_destroy, (cgo_ctx *));
 SYM(int, cgo_ctx_kernel_launches, (cgo_ctx *, int64_t *));
 SYM(int, cgo_obj_rosenbrock_create, (cgo_ctx *, int64_t, cgo_obj **));
+SYM(int, cgo_obj_sparse_ls_create_synthetic, (cgo_ctx *, int64_t, int32_t, int64_t, uint64_t, int32_t, cgo_obj **));
 SYM(int, cgo_obj_destroy, (cgo_obj *));
 SYM(int, cgo_obj_default_x0, (cgo_obj *, uint64_t, double, double *));
 SYM(int, cgo_state_create, (cgo_ctx *, cgo_obj *, const double *, int32_t, cgo_state **, double *));
@@ -49,7 +50,7 @@ static void load(const char *path) {
 #define L(name) do { *(void **)(&p_##name) = dlsym(g_lib, #name); \
         if (!p_##name) { fprintf(stderr, "dlsym(%s) failed\n", #name); exit(2); } } while (0)
     L(cgo_last_error); L(cgo_ctx_create); L(cgo_ctx_destroy); L(cgo_ctx_kernel_launches);
-    L(cgo_obj_rosenbrock_create); L(cgo_obj_destroy); L(cgo_obj_default_x0);
+    L(cgo_obj_rosenbrock_create); L(cgo_obj_sparse_ls_create_synthetic); L(cgo_obj_destroy); L(cgo_obj_default_x0);
     L(cgo_state_create); L(cgo_state_destroy); L(cgo_reset_direction); L(cgo_eval_trial);
     L(cgo_eval_trial_fused_dir); L(cgo_accept); L(cgo_update_dir); L(cgo_download);
 }
@@ -154,7 +155,10 @@ static double beta_hager_zhang(const double *P) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 4) { fprintf(stderr, "usage: host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [perturb]\n"); return 2; }
+    if (argc < 4) {
+        fprintf(stderr, "usage: host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [perturb] [rosenbrock | sparse_ls] [W] [coh_log2]\n");
+        return 2;
+    }
     load(argv[1]);
     const int64_t n = atoll(argv[2]);
     const long max_iters = atol(argv[3]);
@@ -166,9 +170,19 @@ int main(int argc, char **argv) {
     const strong_wolfe lsc = {1e-5, 0.8, 2.0, 1000, 100};
     cgo_ctx *ctx; cgo_obj *obj;
     CHECK(p_cgo_ctx_create(0, NULL, &ctx));
-    CHECK(p_cgo_obj_rosenbrock_create(ctx, n, &obj));
+    /* the objective is the only thing that differs between the configurations: cfg 1 / 2 extended Rosenbrock, cfg 3
+     * the banded-random CSR least squares (10 entries per row, seed 24, x0 = 0: SURVEY.md §8d) */
+    const int sparse_ls = argc > 6 && strcmp(argv[6], "sparse_ls") == 0;
+    if (sparse_ls) {
+        const int64_t W = argc > 7 ? atoll(argv[7]) : ((int64_t)1 << 20);
+        const int32_t coh = argc > 8 ? atoi(argv[8]) : 0;
+        CHECK(p_cgo_obj_sparse_ls_create_synthetic(ctx, n, 10, W, 24, coh, &obj));
+    } else {
+        CHECK(p_cgo_obj_rosenbrock_create(ctx, n, &obj));
+    }
     double *x0 = malloc(sizeof(double) * (size_t)n), *xm = malloc(sizeof(double) * (size_t)n), *gm = malloc(sizeof(double) * (size_t)n);
-    CHECK(p_cgo_obj_default_x0(obj, 24, perturb, x0));
+    if (sparse_ls) memset(x0, 0, sizeof(double) * (size_t)n);
+    else CHECK(p_cgo_obj_default_x0(obj, 24, perturb, x0));
     workspace w;
     memset(&w, 0, sizeof(w));
     CHECK(p_cgo_state_create(ctx, obj, x0, 0, &w.st, w.pack));              /* optim.jl:20-26 */

@@ -64,6 +64,30 @@ def test_c_host_matches_golden_and_oracle(tmp_path):
     assert [int(ln.split()[4]) for ln in lines[:-1]] == [int(v) for v in ora.trace_objective_evals]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("coh", [0, 30])
+def test_c_host_runs_the_csr_least_squares_path(tmp_path, coh):
+    """the same C host on BASELINE.json's headline objective (banded-random CSR least squares; coh 0: sliced layout +
+    k_spmv_direct, coh 30: the TMA-streamed k_csr_rows): whole run bit for bit against the oracle."""
+    import cgoptim_b200 as cg
+    from oracle import oracle as O
+    exe = _build(tmp_path)
+    n, W = 50_000, 4096
+    p = subprocess.run([exe, cg.LIB_PATH, str(n), "1000", "-", "0", "sparse_ls", str(W), str(coh)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    lines = p.stdout.strip().splitlines()
+    ora = O.minimize(O.Objective.sparse_ls(n, 10, W, 24, coh), np.zeros(n),
+                     O.make_config("HagerZhang", "StrongWolfeBisection", eps=1e-5, max_iters=1000, sum_mode="cgo", beta_form="fused"))
+    last = lines[-1].split()
+    assert last[1] == ora.status == "success" and int(last[3]) == ora.iters_ran
+    assert float.fromhex(last[5]) == ora.objective and float.fromhex(last[7]) == ora.minimizer[0]
+    tr = np.array([[float.fromhex(t) for t in ln.split()[1:4]] for ln in lines[:-1]])
+    assert np.array_equal(tr[:, 0], ora.trace_objective) and np.array_equal(tr[:, 1], ora.trace_grad_norm)
+    assert np.array_equal(tr[:, 2], ora.trace_step_size)
+    assert [int(ln.split()[4]) for ln in lines[:-1]] == [int(v) for v in ora.trace_objective_evals]
+
+
 def _c99_hex(v):
     """printf("%a") as glibc prints it (Python's float.hex pads the mantissa: 0x1.8000000000000p+1 vs 0x1.8p+1)"""
     s = float(v).hex()
