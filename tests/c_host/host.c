@@ -10,18 +10,20 @@
  * src/linesearch/nocedal.jl:33-209, getβ(HagerZhang) src/cg_flavours.jl:87-108, updatetrace!
  * src/types.jl:56-71.
  *
- *   host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [x0 perturbation, default 0]
+ *   host <libcgoptim.so> <n> <max_iters> [expected.txt | -] [x0 perturbation, default 0] [rosenbrock | sparse_ls] [W] [coh_log2]
  *
  * prints one line per recorded iteration:  k  f  ‖g‖  a*  evals   (hex floats), then "status <sym> iters <n>".
  * With expected.txt (same line format, written by tests/test_gpu_c_host.py from tests/golden/traces.json)
  * every printed line must match bit for bit; exit code 0 = identical, 3 = mismatch.
  */
+#define _POSIX_C_SOURCE 200809L
 #include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/cgoptim.h"
 
@@ -194,6 +196,8 @@ int main(int argc, char **argv) {
         w.dgu = d[CGO_D_GU]; w.duu = d[CGO_D_UU];
     }
     double a_initial = NAN;
+    struct timespec t_begin, t_end;
+    clock_gettime(CLOCK_MONOTONIC, &t_begin);
     const char *status = "max_iters_reached";
     long iters_ran = max_iters, mismatches = 0, lines = 0;
     char got[256], want[256];
@@ -222,6 +226,9 @@ int main(int argc, char **argv) {
             if (strcmp(got, want) != 0) { mismatches++; fprintf(stderr, "MISMATCH at iteration %ld:\n  got  %s\n  want %s\n", it, got, want); }
         }
     }
+    clock_gettime(CLOCK_MONOTONIC, &t_end);       /* every call returned synchronised: the loop's wall clock is device time + host */
+    const double loop_s = (double)(t_end.tv_sec - t_begin.tv_sec) + 1e-9 * (double)(t_end.tv_nsec - t_begin.tv_nsec);
+    fprintf(stderr, "loop: %ld iterations in %.4f s = %.2f iterations/s\n", iters_ran, loop_s, loop_s > 0 ? (double)iters_ran / loop_s : 0.0);
     CHECK(p_cgo_download(w.st, xm, gm));
     int64_t launches = 0;
     CHECK(p_cgo_ctx_kernel_launches(ctx, &launches));
