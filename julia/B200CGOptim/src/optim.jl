@@ -1,9 +1,11 @@
 # minimizeobjective / minimizeobjectivererun for a device objective: the loop of
 # src/engine/optim.jl:6-208 with every vector line replaced by one ccall (SURVEY.md §3.1).
 
-function CGO.minimizeobjective(fdf!::DeviceObjective, x_initial::Vector{Float64},
+# `x_initial` may be a `DeviceStart` (the iterate of a live workspace: no upload); `keep_workspace = ws -> …` is
+# handed the run's workspace instead of it being closed, so that a restart can begin from it on the device.
+function CGO.minimizeobjective(fdf!::DeviceObjective, x_initial::Union{Vector{Float64},DeviceStart},
                                config::CGConfig{Float64,BT,ET}, linesearch_config::LineSearchConfig;
-                               β_literal::Bool = false) where {BT,ET}
+                               β_literal::Bool = false, keep_workspace::Union{Nothing,Function} = nothing) where {BT,ET}
     max_iters, β_config = config.max_iters, config.β_config                   # :14-17
     lbfgs_m = β_config isa LBFGS ? β_config.m : 0
     info = DeviceWorkspace(fdf!, x_initial; lbfgs_m = lbfgs_m, β_literal = β_literal)   # :20-26, :45
@@ -24,7 +26,7 @@ function CGO.minimizeobjective(fdf!::DeviceObjective, x_initial::Vector{Float64}
         ret.minimizer, ret.gradient = download(info)
         ret.iters_ran, ret.status = i, status
         resizetrace!(ret.trace, i)
-        close!(info)
+        keep_workspace === nothing ? close!(info) : keep_workspace(info)
         ret
     end
 
@@ -51,10 +53,25 @@ end
 function CGO.minimizeobjectivererun(fdf!::DeviceObjective, x_initial::Vector{Float64},
                                     config::CGConfig{Float64,BT,ET}, linesearch_config::LineSearchConfig,
                                     rerun_config_tuples...) where {BT,ET}
-    rets = [minimizeobjective(fdf!, x_initial, config, linesearch_config)]   # :183-188
-    for (rerun_config, backup_linesearch_config) in rerun_config_tuples       # :191
-        rets[end].status == :success && return rets                           # :203
-        push!(rets, minimizeobjective(fdf!, rets[end].minimizer, rerun_config, backup_linesearch_config))  # :195-200
+    # the next attempt starts from rets[end].minimizer (:197): that vector is still on the device, in the previous
+    # attempt's workspace — start from it there (one D2D copy) instead of uploading the host copy
+    live = Any[nothing]
+    keep = ws -> (live[1] === nothing || close!(live[1]); live[1] = ws)
+    try
+        rets = [minimizeobjective(fdf!, x_initial, config, linesearch_config; keep_workspace = keep)]   # :183-188
+        for (rerun_config, backup_linesearch_config) in rerun_config_tuples   # :191
+            rets[end].status == :success && break                             # :203
+            previous = live[1]
+            live[1] = nothing
+            try
+                push!(rets, minimizeobjective(fdf!, DeviceStart(previous), rerun_config, backup_linesearch_config;
+                                              keep_workspace = keep))        # :195-200
+            finally
+                close!(previous)
+            end
+        end
+        return rets
+    finally
+        live[1] === nothing || close!(live[1])
     end
-    return rets
 end
